@@ -1,0 +1,119 @@
+// Internal definitions shared by the host drivers and kernels of libmagma_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "magma_b200.h"
+
+// The opaque queue (replaces control/magma_internal.h:90-211). No cuBLAS/cuSPARSE handles and no
+// 3x65534 pointer scratch: nothing on this path calls a vendor BLAS or displaces pointer arrays.
+struct magma_queue {
+    magma_device_t device;
+    cudaStream_t stream;
+    bool own_stream;
+    // lazily grown per-queue scratch (vbatched statistics, host front-end staging)
+    void *dscratch;
+    size_t dscratch_bytes;
+    void *hscratch;  // pinned
+    size_t hscratch_bytes;
+    // host front ends: two extra streams + events for the H2D / compute / D2H pipeline
+    cudaStream_t aux_stream[2];
+    cudaEvent_t aux_event[8];
+    bool aux_ready;
+};
+
+namespace mb200 {
+
+extern std::atomic<int64_t> g_launches;
+extern int g_tier;  // 0 auto, 1 force small/register tier, 2 force blocked tier
+
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Scratch accessors (grow-only, never shrink; freed with the queue).
+void *queue_dscratch(magma_queue_t q, size_t bytes);
+void *queue_hscratch(magma_queue_t q, size_t bytes);
+
+// Launch error check: the product path fails loudly (no silent fallback).
+#define MB200_CHECK_LAUNCH(name)                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) {                                                         \
+            fprintf(stderr, "libmagma_b200: launch of %s failed: %s\n", name,             \
+                    cudaGetErrorString(e__));                                             \
+            return MAGMA_ERR_UNKNOWN;                                                     \
+        }                                                                                 \
+    } while (0)
+
+#define MB200_CHECK_LAUNCH_VOID(name)                                                     \
+    do {                                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) {                                                         \
+            fprintf(stderr, "libmagma_b200: launch of %s failed: %s\n", name,             \
+                    cudaGetErrorString(e__));                                             \
+        }                                                                                 \
+    } while (0)
+
+// Per-matrix dimensions: uniform (fixed-size batched) or read from device arrays (vbatched).
+struct Dims {
+    int m, n, ldda;            // uniform values, or the maxima in variable mode
+    const int *vm, *vn, *vldda;  // non-null => variable mode
+};
+
+__device__ __forceinline__ void dims_of(const Dims &d, long b, int &m, int &n, int &ld)
+{
+    if (d.vm) {
+        m = d.vm[b];
+        n = d.vn[b];
+        ld = d.vldda[b];
+    } else {
+        m = d.m;
+        n = d.n;
+        ld = d.ldda;
+    }
+}
+
+// ---- kernel launchers implemented in the .cu files -------------------------------------------
+
+// lu_small.cu: whole matrix (m,n <= 32) per warp / half warp / quarter warp, optional fused solve
+// with nrhs right-hand sides (nrhs == 0: factor only). Returns 0, or -100 when the shape is not
+// covered (caller falls through to the blocked tier).
+magma_int_t lu_small_launch(const Dims &d, int max_m, int max_n, double **dA, int **dipiv,
+                            int *dinfo, int nrhs, double **dB, int lddb, long batch,
+                            const int *index_list, cudaStream_t s);
+
+// lu_blocked.cu: blocked right-looking LU for any m x n (two kernels per panel step).
+magma_int_t lu_blocked_launch(const Dims &d, int max_m, int max_n, double **dA, int **dipiv,
+                              int *dinfo, long batch, const int *index_list, cudaStream_t s);
+
+// getrs.cu
+magma_int_t getrs_launch(int trans, int n, int nrhs, double **dA, int ldda, int **dipiv,
+                         double **dB, int lddb, long batch, cudaStream_t s);
+void laswp_rowserial_launch(int n, double **dA, int lda, int k1, int k2, int **dipiv, long batch,
+                            cudaStream_t s);
+void trsm_left_launch(int uplo, int trans, int diag, int m, int n, double alpha, double **dA,
+                      int ldda, double **dB, int lddb, long batch, cudaStream_t s);
+void gemm_nn_launch(int m, int n, int k, double alpha, double const *const *dA, int Ai, int Aj,
+                    int ldda, double const *const *dB, int Bi, int Bj, int lddb, double beta,
+                    double **dC, int Ci, int Cj, int lddc, long batch, cudaStream_t s);
+
+// aux.cu
+void set_pointer_launch(void **out, char *base, long elem, long lda, long row, long col,
+                        long batch_offset, long batch, cudaStream_t s);
+void displace_pointers_launch(void **out, void **in, long elem, long lda, long row, long col,
+                              long batch, cudaStream_t s);
+void memset_int_launch(int *p, int v, long n, cudaStream_t s);
+// vbatched statistics: out[0..7] = {max_m, max_n, max_minmn, max_mxn(clamped), first_bad_arg,
+// count_small, count_total_nonempty, 0}
+void vbatched_stats_launch(const int *m, const int *n, const int *ldda, long batch, int *out8,
+                           cudaStream_t s);
+// builds index lists: small (m,n<=32) first then the rest; counts in out2
+void vbatched_partition_launch(const int *m, const int *n, long batch, int *idx_small,
+                               int *idx_big, int *counts2, cudaStream_t s);
+void dlarnv_launch(uint64_t seed48, int64_t n, double *dx, cudaStream_t s);
+double fp64_peak_run(int kind, cudaStream_t s);
+double hbm_copy_run(size_t bytes, cudaStream_t s);
+
+}  // namespace mb200

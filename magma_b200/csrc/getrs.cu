@@ -1,0 +1,443 @@
+// Batched triangular solves with LU factors: getrs, and the standalone laswp / trsm / gemm entry
+// points the reference declares publicly.
+//
+// Replaces src/zgetrs_batched.cpp:118-178 -- row-serial laswp kernel (nrhs threads per CTA), two
+// recursive trsm drivers (magmablas/ztrsm_batched_core.cpp:33-350: for n=512 each is 16 leaf
+// kernels + 15 cuBLAS gemms, every gemm preceded by three pointer-displacement kernels) or the
+// trsv+gemv recursion (magmablas/ztrsv_batched.cu:65-195) -- with ONE kernel per call:
+// a CTA owns a tile of right-hand sides in shared memory, applies the interchanges while
+// loading it, streams L then U once from HBM/L2 in 32-column blocks (diagonal block solved inside
+// a warp with shuffles, rows below/above updated thread-per-row), and stores X.
+// Arithmetic is the canonical order of oracle/lu_oracle.c (divide by the diagonal).
+#include "common.cuh"
+
+namespace mb200 {
+
+namespace {
+
+constexpr int SOLVE_THREADS = 256;
+constexpr int SB = 32;  // block size along the triangle
+
+// X tile lives in smem as Bs[c*ldb_s + i], i < n, c < tr.
+
+// L (unit or non-unit lower), no transpose: forward substitution.
+template <bool UNIT>
+__device__ void solve_lower_n(int n, int tr, const double *__restrict__ A, int ld, double *Bs, int ldb_s)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = SOLVE_THREADS / 32;
+    for (int kb = 0; kb < n; kb += SB) {
+        const int kw = (n - kb) < SB ? (n - kb) : SB;
+        // diagonal block: warp per rhs column, lane = row
+        if (wid < tr || nw < tr) {
+            double lcol[SB];
+#pragma unroll
+            for (int k = 0; k < SB; ++k)
+                lcol[k] = (k < kw && lane < kw && lane >= k) ? A[(size_t)(kb + lane) + (size_t)(kb + k) * ld] : 0.0;
+            for (int c = wid; c < tr; c += nw) {
+                double x = (lane < kw) ? Bs[c * ldb_s + kb + lane] : 0.0;
+#pragma unroll
+                for (int k = 0; k < SB; ++k) {
+                    if (k < kw) {
+                        if (!UNIT && lane == k) x = x / lcol[k];
+                        const double xk = __shfl_sync(0xffffffffu, x, k);
+                        if (lane > k) x = fma(-lcol[k], xk, x);
+                    }
+                }
+                if (lane < kw) Bs[c * ldb_s + kb + lane] = x;
+            }
+        }
+        __syncthreads();
+        // rows below the block
+        for (int i = kb + kw + tid; i < n; i += SOLVE_THREADS) {
+            double l[SB];
+#pragma unroll
+            for (int k = 0; k < SB; ++k) l[k] = (k < kw) ? A[(size_t)i + (size_t)(kb + k) * ld] : 0.0;
+            for (int c = 0; c < tr; ++c) {
+                double s = Bs[c * ldb_s + i];
+                const double *xk = Bs + c * ldb_s + kb;
+#pragma unroll
+                for (int k = 0; k < SB; ++k)
+                    if (k < kw) s = fma(-l[k], xk[k], s);
+                Bs[c * ldb_s + i] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// U (non-unit or unit upper), no transpose: backward substitution, k decreasing.
+template <bool UNIT>
+__device__ void solve_upper_n(int n, int tr, const double *__restrict__ A, int ld, double *Bs, int ldb_s)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = SOLVE_THREADS / 32;
+    const int nblk = (n + SB - 1) / SB;
+    for (int blk = nblk - 1; blk >= 0; --blk) {
+        const int kb = blk * SB;
+        const int kw = (n - kb) < SB ? (n - kb) : SB;
+        if (wid < tr || nw < tr) {
+            double ucol[SB];
+#pragma unroll
+            for (int k = 0; k < SB; ++k)
+                ucol[k] = (k < kw && lane <= k) ? A[(size_t)(kb + lane) + (size_t)(kb + k) * ld] : 0.0;
+            for (int c = wid; c < tr; c += nw) {
+                double x = (lane < kw) ? Bs[c * ldb_s + kb + lane] : 0.0;
+#pragma unroll
+                for (int k = SB - 1; k >= 0; --k) {
+                    if (k < kw) {
+                        if (!UNIT && lane == k) x = x / ucol[k];
+                        const double xk = __shfl_sync(0xffffffffu, x, k);
+                        if (lane < k) x = fma(-ucol[k], xk, x);
+                    }
+                }
+                if (lane < kw) Bs[c * ldb_s + kb + lane] = x;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < kb; i += SOLVE_THREADS) {
+            double u[SB];
+#pragma unroll
+            for (int k = 0; k < SB; ++k) u[k] = (k < kw) ? A[(size_t)i + (size_t)(kb + k) * ld] : 0.0;
+            for (int c = 0; c < tr; ++c) {
+                double s = Bs[c * ldb_s + i];
+                const double *xk = Bs + c * ldb_s + kb;
+#pragma unroll
+                for (int k = SB - 1; k >= 0; --k)
+                    if (k < kw) s = fma(-u[k], xk[k], s);
+                Bs[c * ldb_s + i] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// U^T (lower-triangular operator): forward. Element (i,k) of U^T is A[k + i*ld].
+template <bool UNIT>
+__device__ void solve_upper_t(int n, int tr, const double *__restrict__ A, int ld, double *Bs, int ldb_s)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = SOLVE_THREADS / 32;
+    for (int kb = 0; kb < n; kb += SB) {
+        const int kw = (n - kb) < SB ? (n - kb) : SB;
+        if (wid < tr || nw < tr) {
+            double tcol[SB];  // tcol[k] = U^T(kb+lane, kb+k) = A[(kb+k) + (kb+lane)*ld], lane >= k
+#pragma unroll
+            for (int k = 0; k < SB; ++k)
+                tcol[k] = (k < kw && lane < kw && lane >= k) ? A[(size_t)(kb + k) + (size_t)(kb + lane) * ld] : 0.0;
+            for (int c = wid; c < tr; c += nw) {
+                double x = (lane < kw) ? Bs[c * ldb_s + kb + lane] : 0.0;
+#pragma unroll
+                for (int k = 0; k < SB; ++k) {
+                    if (k < kw) {
+                        if (!UNIT && lane == k) x = x / tcol[k];
+                        const double xk = __shfl_sync(0xffffffffu, x, k);
+                        if (lane > k) x = fma(-tcol[k], xk, x);
+                    }
+                }
+                if (lane < kw) Bs[c * ldb_s + kb + lane] = x;
+            }
+        }
+        __syncthreads();
+        for (int i = kb + kw + tid; i < n; i += SOLVE_THREADS) {
+            double t[SB];
+#pragma unroll
+            for (int k = 0; k < SB; ++k) t[k] = (k < kw) ? A[(size_t)(kb + k) + (size_t)i * ld] : 0.0;
+            for (int c = 0; c < tr; ++c) {
+                double s = Bs[c * ldb_s + i];
+                const double *xk = Bs + c * ldb_s + kb;
+#pragma unroll
+                for (int k = 0; k < SB; ++k)
+                    if (k < kw) s = fma(-t[k], xk[k], s);
+                Bs[c * ldb_s + i] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// L^T (upper-triangular operator): backward. Element (i,k) of L^T is A[k + i*ld], k > i.
+template <bool UNIT>
+__device__ void solve_lower_t(int n, int tr, const double *__restrict__ A, int ld, double *Bs, int ldb_s)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = SOLVE_THREADS / 32;
+    const int nblk = (n + SB - 1) / SB;
+    for (int blk = nblk - 1; blk >= 0; --blk) {
+        const int kb = blk * SB;
+        const int kw = (n - kb) < SB ? (n - kb) : SB;
+        if (wid < tr || nw < tr) {
+            double tcol[SB];
+#pragma unroll
+            for (int k = 0; k < SB; ++k)
+                tcol[k] = (k < kw && lane <= k) ? A[(size_t)(kb + k) + (size_t)(kb + lane) * ld] : 0.0;
+            for (int c = wid; c < tr; c += nw) {
+                double x = (lane < kw) ? Bs[c * ldb_s + kb + lane] : 0.0;
+#pragma unroll
+                for (int k = SB - 1; k >= 0; --k) {
+                    if (k < kw) {
+                        if (!UNIT && lane == k) x = x / tcol[k];
+                        const double xk = __shfl_sync(0xffffffffu, x, k);
+                        if (lane < k) x = fma(-tcol[k], xk, x);
+                    }
+                }
+                if (lane < kw) Bs[c * ldb_s + kb + lane] = x;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < kb; i += SOLVE_THREADS) {
+            double t[SB];
+#pragma unroll
+            for (int k = 0; k < SB; ++k) t[k] = (k < kw) ? A[(size_t)(kb + k) + (size_t)i * ld] : 0.0;
+            for (int c = 0; c < tr; ++c) {
+                double s = Bs[c * ldb_s + i];
+                const double *xk = Bs + c * ldb_s + kb;
+#pragma unroll
+                for (int k = SB - 1; k >= 0; --k)
+                    if (k < kw) s = fma(-t[k], xk[k], s);
+                Bs[c * ldb_s + i] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// perm[i] = original row that LAPACK's forward interchanges ipiv[0..n) leave at position i
+__device__ void build_perm(int n, const int *__restrict__ ipiv, int *perm, int *sipiv)
+{
+    for (int i = threadIdx.x; i < n; i += SOLVE_THREADS) {
+        perm[i] = i;
+        sipiv[i] = ipiv[i] - 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < n; ++i) {
+            const int p = sipiv[i];
+            if (p != i) {
+                const int t = perm[i];
+                perm[i] = perm[p];
+                perm[p] = t;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// mode: 0 getrs NoTrans, 1 getrs Trans, 2 laswp only (k1..k2), 3.. trsm variants
+__global__ void __launch_bounds__(SOLVE_THREADS)
+getrs_kernel(int trans, int n, int nrhs, int tr_max, double **__restrict__ dA, int ldda, int **__restrict__ dipiv,
+             double **__restrict__ dB, int lddb, int rhs_tiles)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const long b = blockIdx.x / rhs_tiles;
+    const int tile = blockIdx.x % rhs_tiles;
+    const int c0 = tile * tr_max;
+    const int tr = (nrhs - c0) < tr_max ? (nrhs - c0) : tr_max;
+    const int ldb_s = n | 1;  // odd stride: the per-column diagonal-block accesses spread over banks
+    double *Bs = reinterpret_cast<double *>(smem_raw);
+    int *perm = reinterpret_cast<int *>(Bs + (size_t)tr_max * ldb_s);
+    int *sipiv = perm + n;
+    const double *__restrict__ A = dA[b];
+    double *__restrict__ B = dB[b] + (size_t)c0 * lddb;
+
+    build_perm(n, dipiv[b], perm, sipiv);
+    if (trans == MagmaNoTrans) {
+        for (int idx = threadIdx.x; idx < n * tr; idx += SOLVE_THREADS) {
+            const int i = idx % n, c = idx / n;
+            Bs[c * ldb_s + i] = B[perm[i] + (size_t)c * lddb];
+        }
+        __syncthreads();
+        solve_lower_n<true>(n, tr, A, ldda, Bs, ldb_s);
+        solve_upper_n<false>(n, tr, A, ldda, Bs, ldb_s);
+        for (int idx = threadIdx.x; idx < n * tr; idx += SOLVE_THREADS) {
+            const int i = idx % n, c = idx / n;
+            B[i + (size_t)c * lddb] = Bs[c * ldb_s + i];
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < n * tr; idx += SOLVE_THREADS) {
+            const int i = idx % n, c = idx / n;
+            Bs[c * ldb_s + i] = B[i + (size_t)c * lddb];
+        }
+        __syncthreads();
+        solve_upper_t<false>(n, tr, A, ldda, Bs, ldb_s);
+        solve_lower_t<true>(n, tr, A, ldda, Bs, ldb_s);
+        // inverse of the forward interchanges: x[perm[i]] = y[i]
+        for (int idx = threadIdx.x; idx < n * tr; idx += SOLVE_THREADS) {
+            const int i = idx % n, c = idx / n;
+            B[perm[i] + (size_t)c * lddb] = Bs[c * ldb_s + i];
+        }
+    }
+}
+
+// standalone trsm, side = Left.  B <- alpha * op(A)^-1 B
+__global__ void __launch_bounds__(SOLVE_THREADS)
+trsm_left_kernel(int uplo, int trans, int diag, int n, int nrhs, int tr_max, double alpha,
+                 double **__restrict__ dA, int ldda, double **__restrict__ dB, int lddb, int rhs_tiles)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const long b = blockIdx.x / rhs_tiles;
+    const int tile = blockIdx.x % rhs_tiles;
+    const int c0 = tile * tr_max;
+    const int tr = (nrhs - c0) < tr_max ? (nrhs - c0) : tr_max;
+    const int ldb_s = n | 1;
+    double *Bs = reinterpret_cast<double *>(smem_raw);
+    const double *__restrict__ A = dA[b];
+    double *__restrict__ B = dB[b] + (size_t)c0 * lddb;
+    for (int idx = threadIdx.x; idx < n * tr; idx += SOLVE_THREADS) {
+        const int i = idx % n, c = idx / n;
+        Bs[c * ldb_s + i] = alpha * B[i + (size_t)c * lddb];
+    }
+    __syncthreads();
+    const bool unit = (diag == MagmaUnit);
+    const bool lower = (uplo == MagmaLower);
+    const bool nt = (trans == MagmaNoTrans);
+    if (lower && nt) { if (unit) solve_lower_n<true>(n, tr, A, ldda, Bs, ldb_s); else solve_lower_n<false>(n, tr, A, ldda, Bs, ldb_s); }
+    else if (!lower && nt) { if (unit) solve_upper_n<true>(n, tr, A, ldda, Bs, ldb_s); else solve_upper_n<false>(n, tr, A, ldda, Bs, ldb_s); }
+    else if (!lower && !nt) { if (unit) solve_upper_t<true>(n, tr, A, ldda, Bs, ldb_s); else solve_upper_t<false>(n, tr, A, ldda, Bs, ldb_s); }
+    else { if (unit) solve_lower_t<true>(n, tr, A, ldda, Bs, ldb_s); else solve_lower_t<false>(n, tr, A, ldda, Bs, ldb_s); }
+    for (int idx = threadIdx.x; idx < n * tr; idx += SOLVE_THREADS) {
+        const int i = idx % n, c = idx / n;
+        B[i + (size_t)c * lddb] = Bs[c * ldb_s + i];
+    }
+}
+
+// LAPACK-order interchanges k1..k2 (1-based) on n columns; thread per column.
+__global__ void laswp_rowserial_kernel(int n, double **__restrict__ dA, int lda, int k1, int k2,
+                                       int **__restrict__ dipiv, int col_tiles)
+{
+    const long b = blockIdx.x / col_tiles;
+    const int c = (blockIdx.x % col_tiles) * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double *col = dA[b] + (size_t)c * lda;
+    const int *ipiv = dipiv[b];
+    for (int i = k1 - 1; i < k2; ++i) {
+        const int p = ipiv[i] - 1;
+        if (p != i) {
+            const double t = col[i];
+            col[i] = col[p];
+            col[p] = t;
+        }
+    }
+}
+
+// C(Ci.., Cj..) <- alpha A(Ai.., Aj..) B(Bi.., Bj..) + beta C, NoTrans x NoTrans. 32x32 tiles,
+// 16x16 threads, 2x2 per thread; k accumulated in increasing order.
+__global__ void __launch_bounds__(256)
+gemm_nn_kernel(int m, int n, int k, double alpha, double const *const *__restrict__ dA, int Ai, int Aj, int ldda,
+               double const *const *__restrict__ dB, int Bi, int Bj, int lddb, double beta,
+               double **__restrict__ dC, int Ci, int Cj, int lddc, int mt, int nt)
+{
+    __shared__ double As[32][33];
+    __shared__ double Bsm[32][33];
+    const long b = blockIdx.x / (mt * nt);
+    const int t = blockIdx.x % (mt * nt);
+    const int r0 = (t % mt) * 32, c0 = (t / mt) * 32;
+    const double *A = dA[b] + Ai + (size_t)Aj * ldda;
+    const double *B = dB[b] + Bi + (size_t)Bj * lddb;
+    double *C = dC[b] + Ci + (size_t)Cj * lddc;
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    double acc[2][2] = {{0, 0}, {0, 0}};
+    for (int k0 = 0; k0 < k; k0 += 32) {
+        for (int idx = threadIdx.x; idx < 1024; idx += 256) {
+            const int i = idx % 32, kk = idx / 32;
+            As[kk][i] = (r0 + i < m && k0 + kk < k) ? A[(size_t)(r0 + i) + (size_t)(k0 + kk) * ldda] : 0.0;
+            Bsm[i][kk] = (k0 + i < k && c0 + kk < n) ? B[(size_t)(k0 + i) + (size_t)(c0 + kk) * lddb] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < 32; ++kk) {
+            const double a0 = As[kk][tx], a1 = As[kk][tx + 16];
+            const double b0 = Bsm[kk][ty], b1 = Bsm[kk][ty + 16];
+            acc[0][0] = fma(a0, b0, acc[0][0]);
+            acc[1][0] = fma(a1, b0, acc[1][0]);
+            acc[0][1] = fma(a0, b1, acc[0][1]);
+            acc[1][1] = fma(a1, b1, acc[1][1]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int r = r0 + tx + 16 * ii, c = c0 + ty + 16 * jj;
+            if (r < m && c < n) {
+                double *dst = C + (size_t)r + (size_t)c * lddc;
+                *dst = (beta == 0.0) ? alpha * acc[ii][jj] : fma(alpha, acc[ii][jj], beta * (*dst));
+            }
+        }
+}
+
+// rhs columns per CTA such that the tile (+perm, ipiv) fits in shared memory
+int pick_tr(int n, int nrhs, size_t &smem)
+{
+    const size_t cap = 200 * 1024;
+    const int ldb_s = n | 1;
+    int tr = nrhs < 16 ? nrhs : 16;
+    while (tr > 1 && (size_t)tr * ldb_s * 8 + (size_t)n * 8 > cap) tr >>= 1;
+    smem = (size_t)tr * ldb_s * 8 + (size_t)n * 8;
+    return smem <= 227 * 1024 ? tr : 0;
+}
+
+}  // namespace
+
+magma_int_t getrs_launch(int trans, int n, int nrhs, double **dA, int ldda, int **dipiv, double **dB, int lddb,
+                         long batch, cudaStream_t s)
+{
+    size_t smem;
+    const int tr = pick_tr(n, nrhs, smem);
+    if (tr == 0) return MAGMA_ERR_NOT_SUPPORTED;
+    const int rhs_tiles = (nrhs + tr - 1) / tr;
+    const long grid = batch * rhs_tiles;
+    if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaFuncSetAttribute(getrs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_smem = 227 * 1024;
+    }
+    getrs_kernel<<<(unsigned)grid, SOLVE_THREADS, smem, s>>>(trans, n, nrhs, tr, dA, ldda, dipiv, dB, lddb, rhs_tiles);
+    count_launch();
+    MB200_CHECK_LAUNCH("getrs_kernel");
+    return 0;
+}
+
+void laswp_rowserial_launch(int n, double **dA, int lda, int k1, int k2, int **dipiv, long batch, cudaStream_t s)
+{
+    if (n <= 0 || batch <= 0 || k2 < k1) return;
+    const int threads = n < 128 ? ((n + 31) / 32) * 32 : 128;
+    const int col_tiles = (n + threads - 1) / threads;
+    laswp_rowserial_kernel<<<(unsigned)(batch * col_tiles), threads, 0, s>>>(n, dA, lda, k1, k2, dipiv, col_tiles);
+    count_launch();
+    MB200_CHECK_LAUNCH_VOID("laswp_rowserial_kernel");
+}
+
+void trsm_left_launch(int uplo, int trans, int diag, int m, int n, double alpha, double **dA, int ldda,
+                      double **dB, int lddb, long batch, cudaStream_t s)
+{
+    if (m <= 0 || n <= 0 || batch <= 0) return;
+    size_t smem;
+    const int tr = pick_tr(m, n, smem);
+    if (tr == 0) {
+        fprintf(stderr, "libmagma_b200: magmablas_dtrsm_batched: m = %d too large for the shared-memory solver\n", m);
+        return;
+    }
+    const int rhs_tiles = (n + tr - 1) / tr;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(trsm_left_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr = true;
+    }
+    trsm_left_kernel<<<(unsigned)(batch * rhs_tiles), SOLVE_THREADS, smem, s>>>(uplo, trans, diag, m, n, tr, alpha, dA,
+                                                                              ldda, dB, lddb, rhs_tiles);
+    count_launch();
+    MB200_CHECK_LAUNCH_VOID("trsm_left_kernel");
+}
+
+void gemm_nn_launch(int m, int n, int k, double alpha, double const *const *dA, int Ai, int Aj, int ldda,
+                    double const *const *dB, int Bi, int Bj, int lddb, double beta, double **dC, int Ci, int Cj,
+                    int lddc, long batch, cudaStream_t s)
+{
+    if (m <= 0 || n <= 0 || batch <= 0) return;
+    const int mt = (m + 31) / 32, nt = (n + 31) / 32;
+    gemm_nn_kernel<<<(unsigned)(batch * mt * nt), 256, 0, s>>>(m, n, k, alpha, dA, Ai, Aj, ldda, dB, Bi, Bj, lddb,
+                                                             beta, dC, Ci, Cj, lddc, mt, nt);
+    count_launch();
+    MB200_CHECK_LAUNCH_VOID("gemm_nn_kernel");
+}
+
+}  // namespace mb200

@@ -1,0 +1,201 @@
+"""oracle/ -- TEST INFRASTRUCTURE ONLY.
+
+CPU checker for the batched FP64 LU path: `lu_oracle.c` (the restated arithmetic) and
+`lapack_loop.c` (the reference testers' host-LAPACK OpenMP loop, dlopen'ing the OpenBLAS that
+scipy bundles). Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this package; nothing under magma_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+
+MagmaNoTrans, MagmaTrans, MagmaConjTrans = 111, 112, 113
+
+
+def _compile(src: str, out: str, extra=()):
+    os.makedirs(_BUILD, exist_ok=True)
+    srcp = os.path.join(_HERE, src)
+    outp = os.path.join(_BUILD, out)
+    if os.path.exists(outp) and os.path.getmtime(outp) >= os.path.getmtime(srcp):
+        return outp
+    cmd = ["gcc", "-O3", "-mavx2", "-mfma", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC",
+           "-o", outp + ".tmp", srcp, "-lm", *extra]
+    subprocess.run(cmd, check=True)
+    os.replace(outp + ".tmp", outp)
+    return outp
+
+
+def build():
+    """Compile both checker libraries (idempotent). Returns their paths."""
+    return (_compile("lu_oracle.c", "liblu_oracle.so"),
+            _compile("lapack_loop.c", "liblapack_loop.so", extra=("-ldl",)))
+
+
+_lib = None
+_lap = None
+
+_i, _l, _d = C.c_int, C.c_long, C.c_double
+_pd = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_pi = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_pl = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build()[0])
+        L.oracle_dlarnv_uniform01.argtypes = [_pi, _l, _pd]
+        L.oracle_dgetf2.argtypes = [_i, _i, _pd, _i, _pi]
+        L.oracle_dgetf2.restype = _i
+        L.oracle_dgetrs.argtypes = [_i, _i, _i, _pd, _i, _pi, _pd, _i]
+        L.oracle_dgesv.argtypes = [_i, _i, _pd, _i, _pi, _pd, _i]
+        L.oracle_dgesv.restype = _i
+        L.oracle_dgetrf_batched.argtypes = [_i, _i, _pd, _i, _l, _pi, _l, _pi, _l]
+        L.oracle_dgetrs_batched.argtypes = [_i, _i, _i, _pd, _i, _l, _pi, _l, _pd, _i, _l, _l]
+        L.oracle_dgesv_batched.argtypes = [_i, _i, _pd, _i, _l, _pi, _l, _pd, _i, _l, _pi, _l]
+        L.oracle_dgetrf_vbatched.argtypes = [_pi, _pi, _pd, _pi, _pl, _pi, _pl, _pi, _l]
+        L.oracle_lu_backward_error.argtypes = [_i, _i, _pd, _i, _pd, _i, _pi]
+        L.oracle_lu_backward_error.restype = _d
+        L.oracle_solve_residual.argtypes = [_i, _i, _i, _pd, _i, _pd, _i, _pd, _i]
+        L.oracle_solve_residual.restype = _d
+        L.oracle_lu_backward_error_batched.argtypes = [_i, _i, _pd, _i, _l, _pd, _i, _l, _pi, _l, _l]
+        L.oracle_lu_backward_error_batched.restype = _d
+        L.oracle_solve_residual_batched.argtypes = [_i, _i, _i, _pd, _i, _l, _pd, _i, _l, _pd, _i,
+                                                    _l, _l]
+        L.oracle_solve_residual_batched.restype = _d
+        L.oracle_num_threads.restype = _i
+        _lib = L
+    return _lib
+
+
+def find_host_lapack() -> str:
+    """Path of the OpenBLAS scipy bundles (the host LAPACK available in this image)."""
+    import scipy
+    cands = glob.glob(os.path.join(os.path.dirname(scipy.__file__), "..", "scipy.libs",
+                                   "libscipy_openblas*.so"))
+    if not cands:
+        raise RuntimeError("host LAPACK (scipy's OpenBLAS) not found")
+    return os.path.realpath(cands[0])
+
+
+def lapack():
+    global _lap
+    if _lap is None:
+        L = C.CDLL(build()[1])
+        L.lapack_loop_init.argtypes = [C.c_char_p]
+        L.lapack_loop_init.restype = _i
+        L.lapack_loop_describe.restype = C.c_char_p
+        L.lapack_loop_threads.restype = _i
+        rc = L.lapack_loop_init(find_host_lapack().encode())
+        if rc != 0:
+            raise RuntimeError("lapack_loop_init: " + L.lapack_loop_describe().decode())
+        L.lapack_dlarnv.argtypes = [_i, _pi, _l, _pd]
+        L.lapack_dgetrf_loop.argtypes = [_i, _i, _pd, _i, _l, _pi, _l, _pi, _l]
+        L.lapack_dgetrf_loop.restype = _d
+        L.lapack_dgetrs_loop.argtypes = [_i, _i, _i, _pd, _i, _l, _pi, _l, _pd, _i, _l, _l]
+        L.lapack_dgetrs_loop.restype = _d
+        L.lapack_dgesv_loop.argtypes = [_i, _i, _pd, _i, _l, _pi, _l, _pd, _i, _l, _pi, _l]
+        L.lapack_dgesv_loop.restype = _d
+        L.lapack_dgetrf_vloop.argtypes = [_pi, _pi, _pd, _pi, _pl, _pi, _pl, _pi, _l]
+        L.lapack_dgetrf_vloop.restype = _d
+        _lap = L
+    return _lap
+
+
+# --------------------------------------------------------------------------------------------
+# numpy-level helpers. Batches are stored as arrays of shape (batch, ncols, ld): element
+# [b, j, i] is A_b(i, j), i.e. each matrix is column-major with leading dimension ld.
+# --------------------------------------------------------------------------------------------
+
+def dlarnv(n: int, iseed=None) -> tuple[np.ndarray, np.ndarray]:
+    """The testers' input stream: dlarnv(idist=1, ISEED={0,0,0,1}). Returns (x, next_seed)."""
+    seed = np.array([0, 0, 0, 1] if iseed is None else iseed, dtype=np.int32)
+    x = np.empty(n, dtype=np.float64)
+    lib().oracle_dlarnv_uniform01(seed, n, x)
+    return x, seed
+
+
+def random_batch(batch: int, m: int, n: int, ld: int | None = None, iseed=None):
+    """batch matrices m x n drawn back-to-back (lda=m) from the dlarnv stream, then laid out
+    with leading dimension ld (padding rows are zero). Returns (A[batch,n,ld], next_seed)."""
+    ld = m if ld is None else ld
+    x, seed = dlarnv(batch * m * n, iseed)
+    A = np.zeros((batch, n, ld), dtype=np.float64)
+    A[:, :, :m] = x.reshape(batch, n, m)
+    return A, seed
+
+
+def getrf_batched(A: np.ndarray, m: int):
+    """In-place LU of A[batch, n, ld] (m rows used). Returns (ipiv[batch, min(m,n)], info)."""
+    batch, n, ld = A.shape
+    mn = min(m, n)
+    ipiv = np.zeros((batch, max(mn, 1)), dtype=np.int32)
+    info = np.zeros(batch, dtype=np.int32)
+    lib().oracle_dgetrf_batched(m, n, A.reshape(-1), ld, n * ld, ipiv.reshape(-1), max(mn, 1),
+                                info, batch)
+    return ipiv[:, :mn], info
+
+
+def getrs_batched(trans: int, LU: np.ndarray, ipiv: np.ndarray, B: np.ndarray, n: int):
+    batch, _, lda = LU.shape
+    _, nrhs, ldb = B.shape
+    ip = np.ascontiguousarray(ipiv, dtype=np.int32)
+    lib().oracle_dgetrs_batched(trans, n, nrhs, LU.reshape(-1), lda, LU.shape[1] * lda,
+                                ip.reshape(-1), ip.shape[1], B.reshape(-1), ldb, nrhs * ldb, batch)
+
+
+def gesv_batched(A: np.ndarray, B: np.ndarray, n: int):
+    batch, _, lda = A.shape
+    _, nrhs, ldb = B.shape
+    ipiv = np.zeros((batch, n), dtype=np.int32)
+    info = np.zeros(batch, dtype=np.int32)
+    lib().oracle_dgesv_batched(n, nrhs, A.reshape(-1), lda, A.shape[1] * lda, ipiv.reshape(-1), n,
+                               B.reshape(-1), ldb, nrhs * ldb, info, batch)
+    return ipiv, info
+
+
+def lu_backward_error(A0: np.ndarray, LU: np.ndarray, ipiv: np.ndarray, m: int) -> float:
+    """max over the batch of ||P A0 - L U||_F / (||A0||_F n)."""
+    batch, n, ld0 = A0.shape
+    ip = np.ascontiguousarray(ipiv, dtype=np.int32)
+    return lib().oracle_lu_backward_error_batched(
+        m, n, np.ascontiguousarray(A0).reshape(-1), ld0, n * ld0,
+        np.ascontiguousarray(LU).reshape(-1), LU.shape[2], n * LU.shape[2],
+        ip.reshape(-1), ip.shape[1], batch)
+
+
+def solve_residual(trans: int, A0: np.ndarray, X: np.ndarray, B0: np.ndarray, n: int) -> float:
+    batch, _, lda = A0.shape
+    _, nrhs, ldx = X.shape
+    return lib().oracle_solve_residual_batched(
+        trans, n, nrhs, np.ascontiguousarray(A0).reshape(-1), lda, A0.shape[1] * lda,
+        np.ascontiguousarray(X).reshape(-1), ldx, nrhs * ldx,
+        np.ascontiguousarray(B0).reshape(-1), B0.shape[2], nrhs * B0.shape[2], batch)
+
+
+EPS = float(np.finfo(np.float64).eps) / 2  # LAPACK dlamch('E') = 2^-53, as the testers use
+TOL = 30 * EPS                              # testing/magma_util.cpp:192
+
+
+def flops_getrf(m: float, n: float) -> float:
+    """FLOPS_DGETRF, testing/flops.h:79-84,274 (fmuls + fadds)."""
+    if m < n:
+        mul = 0.5 * m * (m * (n - (1.0 / 3.0) * m - 1.0) + n) + (2.0 / 3.0) * m
+        add = 0.5 * m * (m * (n - (1.0 / 3.0) * m) - n) + (1.0 / 6.0) * m
+    else:
+        mul = 0.5 * n * (n * (m - (1.0 / 3.0) * n - 1.0) + m) + (2.0 / 3.0) * n
+        add = 0.5 * n * (n * (m - (1.0 / 3.0) * n) - m) + (1.0 / 6.0) * n
+    return mul + add
+
+
+def flops_getrs(n: float, nrhs: float) -> float:
+    """FLOPS_DGETRS, testing/flops.h:90-91,284."""
+    return nrhs * n * n + nrhs * n * (n - 1)

@@ -1,0 +1,150 @@
+"""CPU tests: pin oracle/lu_oracle.c against (1) the committed LAPACK golden vectors, (2) the
+known-answer values recorded in SURVEY.md section 8c, (3) the host LAPACK itself (the reference
+testers' CPU path) on fresh dlarnv streams, and check the checker's own error formulas."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "lu_golden.npz"))
+SHAPES = sorted({k.rsplit("_", 1)[0] for k in GOLD.files if k.endswith("_A")})
+
+
+def _shape(key):
+    m, n, r = key.split("_")
+    return int(m[1:]), int(n[1:]), int(r[1:])
+
+
+def test_dlarnv_known_answer():
+    # dlarnv(1,{0,0,0,1}) -> 0.12062469795087694, 0.64384591082168541
+    x, seed = oracle.dlarnv(2)
+    assert x[0] == 0.12062469795087694 and x[1] == 0.64384591082168541
+    assert np.array_equal(GOLD["first_two"], x)
+
+
+def test_dlarnv_matches_lapack_stream():
+    L = oracle.lapack()
+    seed = np.array([0, 0, 0, 1], dtype=np.int32)
+    y = np.empty(300001)
+    L.lapack_dlarnv(1, seed, y.size, y)
+    x, s2 = oracle.dlarnv(y.size)
+    assert np.array_equal(x, y) and np.array_equal(seed, s2)
+    # continuing the stream from the returned seed
+    y2 = np.empty(1000)
+    L.lapack_dlarnv(1, seed, y2.size, y2)
+    x2, _ = oracle.dlarnv(1000, s2)
+    assert np.array_equal(x2, y2)
+
+
+def test_known_answer_4x4():
+    # the first 4x4 of the stream factors with ipiv = 2 3 3 4, info = 0
+    A, _ = oracle.random_batch(1, 4, 4)
+    ipiv, info = oracle.getrf_batched(A, 4)
+    assert ipiv.tolist() == [[2, 3, 3, 4]] and info.tolist() == [0]
+
+
+@pytest.mark.parametrize("key", SHAPES)
+def test_oracle_vs_golden(key):
+    m, n, nrhs = _shape(key)
+    A0 = GOLD[key + "_A"]
+    A = A0.copy()
+    if nrhs:
+        B = GOLD[key + "_B"].copy()
+        ipiv, info = oracle.gesv_batched(A, B, n)
+        X = GOLD[key + "_X"]
+        assert np.allclose(B, X, rtol=1e-9, atol=1e-11)
+        assert oracle.solve_residual(oracle.MagmaNoTrans, A0, B, GOLD[key + "_B"], n) < oracle.TOL
+    else:
+        ipiv, info = oracle.getrf_batched(A, m)
+    assert np.array_equal(ipiv, GOLD[key + "_ipiv"]), "pivots differ from LAPACK"
+    assert np.array_equal(info, GOLD[key + "_info"])
+    # factors agree with LAPACK's up to rounding-order differences
+    ref = GOLD[key + "_LU"]
+    assert np.max(np.abs(A - ref)) <= 1e-10 * max(1.0, np.max(np.abs(ref)))
+    assert oracle.lu_backward_error(A0, A, ipiv, m) < oracle.TOL
+    assert oracle.lu_backward_error(A0, ref, GOLD[key + "_ipiv"], m) < oracle.TOL
+
+
+@pytest.mark.parametrize("m,n,batch", [(16, 16, 3000), (32, 32, 1500), (7, 7, 500), (50, 20, 200), (20, 50, 200),
+                                       (128, 128, 40), (257, 257, 4)])
+def test_pivots_identical_to_host_lapack(m, n, batch):
+    L = oracle.lapack()
+    A, _ = oracle.random_batch(batch, m, n, iseed=[1, 2, 3, 5])
+    A0 = A.copy()
+    ipiv, info = oracle.getrf_batched(A, m)
+    mn = min(m, n)
+    LU = A0.copy()
+    ip2 = np.zeros((batch, mn), np.int32)
+    inf2 = np.zeros(batch, np.int32)
+    L.lapack_dgetrf_loop(m, n, LU.reshape(-1), m, m * n, ip2.reshape(-1), mn, inf2, batch)
+    assert np.array_equal(ipiv, ip2)
+    assert np.array_equal(info, inf2)
+    assert oracle.lu_backward_error(A0, A, ipiv, m) < oracle.TOL
+
+
+def test_getrs_trans_and_notrans_vs_lapack():
+    L = oracle.lapack()
+    n, nrhs, batch = 40, 3, 20
+    A, seed = oracle.random_batch(batch, n, n)
+    B, _ = oracle.random_batch(batch, n, nrhs, iseed=seed)
+    LU = A.copy()
+    ipiv, _ = oracle.getrf_batched(LU, n)
+    for trans in (oracle.MagmaNoTrans, oracle.MagmaTrans):
+        X = B.copy()
+        oracle.getrs_batched(trans, LU, ipiv, X, n)
+        X2 = B.copy()
+        L.lapack_dgetrs_loop(trans, n, nrhs, LU.reshape(-1), n, n * n, ipiv.reshape(-1), n, X2.reshape(-1), n,
+                             n * nrhs, batch)
+        assert np.allclose(X, X2, rtol=1e-9, atol=1e-11)
+        assert oracle.solve_residual(trans, A, X, B, n) < oracle.TOL
+
+
+def test_singular_and_tie_semantics():
+    # zero matrix: info = 1, ipiv = identity, nothing scaled (smallsq_noshfl.cu:90-91,106)
+    Z = np.zeros((1, 5, 5))
+    ipiv, info = oracle.getrf_batched(Z, 5)
+    assert info.tolist() == [1] and ipiv.tolist() == [[1, 2, 3, 4, 5]] and not Z.any()
+    # all ones: every column ties, LAPACK's idamax takes the first -> ipiv = identity, info = 2
+    O = np.ones((1, 4, 4))
+    ipiv, info = oracle.getrf_batched(O, 4)
+    L = oracle.lapack()
+    O2 = np.ones(16)
+    ip2 = np.zeros(4, np.int32)
+    inf2 = np.zeros(1, np.int32)
+    L.lapack_dgetrf_loop(4, 4, O2, 4, 16, ip2, 4, inf2, 1)
+    assert ipiv.reshape(-1).tolist() == ip2.tolist() and info.tolist() == inf2.tolist() == [2]
+    # a zero column in the middle
+    A, _ = oracle.random_batch(1, 6, 6)
+    A[0, 2, :] = 0.0
+    A2 = A.copy().reshape(-1)
+    ipiv, info = oracle.getrf_batched(A, 6)
+    ip2 = np.zeros(6, np.int32)
+    L.lapack_dgetrf_loop(6, 6, A2, 6, 36, ip2, 6, inf2, 1)
+    assert info.tolist() == inf2.tolist() == [3] and ipiv.reshape(-1).tolist() == ip2.tolist()
+
+
+def test_checker_detects_errors():
+    A, _ = oracle.random_batch(4, 12, 12)
+    LU = A.copy()
+    ipiv, _ = oracle.getrf_batched(LU, 12)
+    assert oracle.lu_backward_error(A, LU, ipiv, 12) < oracle.TOL
+    bad = LU.copy()
+    bad[2, 5, 7] += 1e-6
+    assert oracle.lu_backward_error(A, bad, ipiv, 12) > oracle.TOL
+    bad = LU.copy()
+    bad[1, 0, 0] = np.nan
+    assert oracle.lu_backward_error(A, bad, ipiv, 12) > oracle.TOL
+    badp = ipiv.copy()
+    badp[0, 0], badp[0, 1] = 12, 12
+    assert oracle.lu_backward_error(A, LU, badp, 12) > oracle.TOL
+
+
+def test_flops_formulas():
+    # testing/flops.h:79-91 evaluated at the BASELINE.md sizes
+    assert round(oracle.flops_getrf(32, 32)) == 21360
+    assert round(oracle.flops_getrf(128, 128)) == 1390016
+    assert round(oracle.flops_getrf(512, 512)) == 89347840
+    assert oracle.flops_getrs(512, 16) == 8380416
+    assert round(oracle.flops_getrf(16, 16)) == 2616 and oracle.flops_getrs(16, 1) == 496

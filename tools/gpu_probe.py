@@ -10,6 +10,9 @@ def flops_getrf(n):
     add = 0.5 * n * (n * (m - n / 3.0) - m) + n / 6.0
     return mul + add
 
+import os
+CONFIGS=[(32, 10000, 0), (32, 400000, 0), (16, 1000000, 1), (16, 1000000, 0), (8, 2000000, 0), (24, 400000, 0), (64, 100000, 0), (128, 50000, 0), (256, 8000, 0), (512, 4000, 0)]
+if os.environ.get('PROBE_SMALL'): CONFIGS=[c for c in CONFIGS if c[0]<=32]
 def main():
     torch.cuda.set_device(0)
     mb.magma_init()
@@ -28,8 +31,7 @@ def main():
             e0.record(); fn(); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         return min(ts), float(np.median(ts))
-    for (n, batch, nrhs) in [(32, 10000, 0), (32, 400000, 0), (16, 1000000, 1), (16, 1000000, 0), (8, 2000000, 0),
-                             (64, 100000, 0), (128, 50000, 0), (256, 8000, 0), (512, 4000, 0)]:
+    for (n, batch, nrhs) in CONFIGS:
         db = mb.DeviceBatch(batch, n, n, nrhs=max(nrhs, 0) or 0, queue=q) if nrhs else mb.DeviceBatch(batch, n, n, queue=q)
         seed = np.array([0, 0, 0, 1], dtype=np.int32)
         mb.dlarnv_uniform(seed, batch * n * n, db.A, q)

@@ -302,6 +302,8 @@ double magma_b200_hbm_copy_gbs(size_t bytes, magma_queue_t queue);
 int64_t magma_b200_launch_count(void);
 /* Force a tier for tests/benches: 0 = auto, 1 = register/warp (small), 2 = blocked. */
 void magma_b200_set_tier(int tier);
+/* Register tier layout override for tuning sweeps: rows per lane (1 or 2), 0 = tuned default. */
+void magma_b200_set_small_rows(int rows);
 
 /* F77-style by-reference wrappers in the control/magma_df77.cpp convention (device pointers
  * passed as integer handles). New surface: the generated reference layer has no batched LU. */

@@ -28,7 +28,7 @@ __all__ = [
     "magma_dgetrf_vbatched_max_nocheck_work", "magma_dgetrf_batched_smallsq_noshfl",
     "magma_dgesv_batched_small", "magma_dset_pointer", "magma_iset_pointer", "magma_ddisplace_pointers",
     "magma_dlaswp_rowserial_batched", "magmablas_dtrsm_batched", "magma_dgemm_batched_core",
-    "magma_get_dgetrf_batched_nbparam", "dlarnv_uniform", "set_tier", "launch_count",
+    "magma_get_dgetrf_batched_nbparam", "dlarnv_uniform", "set_tier", "set_small_rows", "launch_count",
     "fp64_peak_tflops", "hbm_copy_gbs", "DeviceBatch", "dgetrf_batched_host", "dgesv_batched_host",
 ]
 
@@ -189,6 +189,10 @@ def dlarnv_uniform(iseed, n: int, dx, queue):
 
 def set_tier(tier: int):
     _lib.load().magma_b200_set_tier(tier)
+
+
+def set_small_rows(rows: int):
+    _lib.load().magma_b200_set_small_rows(rows)
 
 
 def launch_count() -> int:

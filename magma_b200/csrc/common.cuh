@@ -29,6 +29,7 @@ namespace mb200 {
 
 extern std::atomic<int64_t> g_launches;
 extern int g_tier;  // 0 auto, 1 force small/register tier, 2 force blocked tier
+extern int g_small_rows;  // register tier: rows per lane, 0 = tuned default
 
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

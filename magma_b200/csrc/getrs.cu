@@ -8,7 +8,8 @@
 // a CTA owns a tile of right-hand sides in shared memory, applies the interchanges while
 // loading it, streams L then U once from HBM/L2 in 32-column blocks (diagonal block solved inside
 // a warp with shuffles, rows below/above updated thread-per-row), and stores X.
-// Arithmetic is the canonical order of oracle/lu_oracle.c (divide by the diagonal).
+// Arithmetic is the canonical order of oracle/lu_oracle.c (multiply by the inverted diagonal, as
+// the reference's trsm does: magmablas/trsm_template_device.cuh:54-58).
 #include "common.cuh"
 
 namespace mb200 {
@@ -33,12 +34,13 @@ __device__ void solve_lower_n(int n, int tr, const double *__restrict__ A, int l
 #pragma unroll
             for (int k = 0; k < SB; ++k)
                 lcol[k] = (k < kw && lane < kw && lane >= k) ? A[(size_t)(kb + lane) + (size_t)(kb + k) * ld] : 0.0;
+            const double dinv = (!UNIT && lane < kw) ? 1.0 / A[(size_t)(kb + lane) * (ld + 1)] : 1.0;
             for (int c = wid; c < tr; c += nw) {
                 double x = (lane < kw) ? Bs[c * ldb_s + kb + lane] : 0.0;
 #pragma unroll
                 for (int k = 0; k < SB; ++k) {
                     if (k < kw) {
-                        if (!UNIT && lane == k) x = x / lcol[k];
+                        if (!UNIT && lane == k) x = x * dinv;
                         const double xk = __shfl_sync(0xffffffffu, x, k);
                         if (lane > k) x = fma(-lcol[k], xk, x);
                     }
@@ -79,12 +81,13 @@ __device__ void solve_upper_n(int n, int tr, const double *__restrict__ A, int l
 #pragma unroll
             for (int k = 0; k < SB; ++k)
                 ucol[k] = (k < kw && lane <= k) ? A[(size_t)(kb + lane) + (size_t)(kb + k) * ld] : 0.0;
+            const double dinv = (!UNIT && lane < kw) ? 1.0 / A[(size_t)(kb + lane) * (ld + 1)] : 1.0;
             for (int c = wid; c < tr; c += nw) {
                 double x = (lane < kw) ? Bs[c * ldb_s + kb + lane] : 0.0;
 #pragma unroll
                 for (int k = SB - 1; k >= 0; --k) {
                     if (k < kw) {
-                        if (!UNIT && lane == k) x = x / ucol[k];
+                        if (!UNIT && lane == k) x = x * dinv;
                         const double xk = __shfl_sync(0xffffffffu, x, k);
                         if (lane < k) x = fma(-ucol[k], xk, x);
                     }
@@ -122,12 +125,13 @@ __device__ void solve_upper_t(int n, int tr, const double *__restrict__ A, int l
 #pragma unroll
             for (int k = 0; k < SB; ++k)
                 tcol[k] = (k < kw && lane < kw && lane >= k) ? A[(size_t)(kb + k) + (size_t)(kb + lane) * ld] : 0.0;
+            const double dinv = (!UNIT && lane < kw) ? 1.0 / A[(size_t)(kb + lane) * (ld + 1)] : 1.0;
             for (int c = wid; c < tr; c += nw) {
                 double x = (lane < kw) ? Bs[c * ldb_s + kb + lane] : 0.0;
 #pragma unroll
                 for (int k = 0; k < SB; ++k) {
                     if (k < kw) {
-                        if (!UNIT && lane == k) x = x / tcol[k];
+                        if (!UNIT && lane == k) x = x * dinv;
                         const double xk = __shfl_sync(0xffffffffu, x, k);
                         if (lane > k) x = fma(-tcol[k], xk, x);
                     }
@@ -167,12 +171,13 @@ __device__ void solve_lower_t(int n, int tr, const double *__restrict__ A, int l
 #pragma unroll
             for (int k = 0; k < SB; ++k)
                 tcol[k] = (k < kw && lane <= k) ? A[(size_t)(kb + k) + (size_t)(kb + lane) * ld] : 0.0;
+            const double dinv = (!UNIT && lane < kw) ? 1.0 / A[(size_t)(kb + lane) * (ld + 1)] : 1.0;
             for (int c = wid; c < tr; c += nw) {
                 double x = (lane < kw) ? Bs[c * ldb_s + kb + lane] : 0.0;
 #pragma unroll
                 for (int k = SB - 1; k >= 0; --k) {
                     if (k < kw) {
-                        if (!UNIT && lane == k) x = x / tcol[k];
+                        if (!UNIT && lane == k) x = x * dinv;
                         const double xk = __shfl_sync(0xffffffffu, x, k);
                         if (lane < k) x = fma(-tcol[k], xk, x);
                     }

@@ -424,5 +424,6 @@ magma_int_t *magma_ioffset_2d(magma_int_t *A, magma_int_t lda, magma_int_t i, ma
 
 int64_t magma_b200_launch_count(void) { return g_launches.load(); }
 void magma_b200_set_tier(int tier) { g_tier = tier; }
+void magma_b200_set_small_rows(int rows) { g_small_rows = rows; }
 
 }  // extern "C"

@@ -13,7 +13,8 @@
  *   - blocked driver whose result this must equal   src/zgetrf_batched.cpp:81-213
  *   - solve = row interchanges, unit-lower forward, non-unit-upper backward
  *                                                   src/zgetrs_batched.cpp:118-146
- *   - fused small gesv (divide by the diagonal)     magmablas/zgesv_batched_small.cu:47-116
+ *   - fused small gesv                              magmablas/zgesv_batched_small.cu:47-116
+ *   - trsm: multiply by the inverted diagonal       magmablas/trsm_template_device.cuh:54-58
  *   - input stream dlarnv(1, {0,0,0,1})             testing/testing_zgetrf_batched.cpp:136,180
  *   - checks ||PA-LU||_F/(n ||A||_F), residual      testing/testing_zgetrf_batched.cpp:41-81,
  *                                                   testing/testing_zgesv_batched.cpp:133-153
@@ -150,7 +151,10 @@ static void apply_pivots(int k, int nrhs, double *B, int ldb, const int *ipiv, i
  * Solve with the factors. trans: 111 NoTrans, 112 Trans, 113 ConjTrans (MAGMA enum values,
  * include/magma_types.h:612-614). Canonical order:
  *   NoTrans  forward : b(i) <- fma(-l(i,k), b(k), b(i)) for k increasing;
- *            backward: for k = n-1..0: b(k) <- b(k)/u(k,k); b(i) <- fma(-u(i,k), b(k), b(i)), i<k.
+ *            backward: for k = n-1..0: b(k) <- b(k)*(1/u(k,k)); b(i) <- fma(-u(i,k), b(k), b(i)), i<k.
+ *            The diagonal is inverted once and multiplied, as the reference's batched trsm does
+ *            (magmablas/trsm_template_device.cuh:54-58,143); its fused n<=32 gesv kernel divides
+ *            instead (magmablas/zgesv_batched_small.cu:111) -- one rule is used everywhere here.
  *   Trans    LAPACK dgetrs('T'): solve U^T (non-unit) forward, L^T (unit) backward, then the
  *            interchanges in reverse. (The reference's batched Trans branch swaps the diag flags
  *            and applies the interchanges forward, src/zgetrs_batched.cpp:148-178; that is a
@@ -171,7 +175,7 @@ void oracle_dgetrs(int trans, int n, int nrhs, const double *A, int lda, const i
             }
             for (int k = n - 1; k >= 0; --k) {
                 const double *ck = A + (size_t)k * lda;
-                double bk = b[k] / ck[k];
+                double bk = b[k] * (1.0 / ck[k]); /* reciprocal of the diagonal, as the reference's trsm */
                 b[k] = bk;
                 for (int i = 0; i < k; ++i) b[i] = fma(-ck[i], bk, b[i]);
             }
@@ -184,7 +188,7 @@ void oracle_dgetrs(int trans, int n, int nrhs, const double *A, int lda, const i
                 const double *ci = A + (size_t)i * lda;
                 double s = b[i];
                 for (int k = 0; k < i; ++k) s = fma(-ci[k], b[k], s);
-                b[i] = s / ci[i];
+                b[i] = s * (1.0 / ci[i]);
             }
             /* L^T x = y (unit) */
             for (int i = n - 1; i >= 0; --i) {

@@ -17,6 +17,7 @@ def main():
     torch.cuda.set_device(0)
     mb.magma_init()
     q = mb.Queue.from_torch(0)
+    if os.environ.get('SMALL_ROWS'): mb.set_small_rows(int(os.environ['SMALL_ROWS']))
     out = {}
     out["dfma_tflops"] = mb.fp64_peak_tflops(0, q)
     out["dmma_tflops"] = mb.fp64_peak_tflops(1, q)

@@ -26,6 +26,7 @@ print("-- stall reasons (warps stalled per issue) --")
 for k, v in st[:8]: print(f"   {k.replace('smsp__average_warps_issue_stalled_','').replace('smsp__average_warp_latency_issue_stalled_','lat_'):60s} {v:8.3f}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
+rows = [r for r in rows if len(r) > 5]
 if rows:
     h = rows[0]
     def col(name):
@@ -38,4 +39,17 @@ if rows:
         tot = sum(float(r[cs] or 0) for r in rows[1:] if len(r) > cs)
         top = sorted(rows[1:], key=lambda r: -float(r[cs] or 0))[:nl]
         print(f"-- hottest SASS by stall samples (total {tot:.0f}) --")
-        for r in top: print(f"   {float(r[cs] or 0)/max(tot,1)*100:5.1f}%  x{r[cx] if cx is not None else ''}  {r[ci][:110]}")
+        names = [x for x in h if x.startswith("stall_") and "Not Issued" not in x]
+        idx = {x: h.index(x) for x in names}
+        for r in top:
+            why = sorted(((float(r[idx[x]] or 0), x) for x in names), reverse=True)[:2]
+            print(f"   {float(r[cs] or 0)/max(tot,1)*100:5.1f}%  x{r[cx] if cx is not None else ''}  {r[ci].strip()[:70]:70s} {why[0][1]}={why[0][0]:.0f} {why[1][1]}={why[1][0]:.0f}")
+        # aggregate by opcode
+        agg = collections.defaultdict(float)
+        for r in rows[1:]:
+            op = r[ci].strip().split()
+            if not op: continue
+            o = op[1] if op[0].startswith('@') and len(op) > 1 else op[0]
+            agg[o.rstrip(';')] += float(r[cs] or 0)
+        print("-- stall samples by opcode --")
+        for o, v in sorted(agg.items(), key=lambda t: -t[1])[:14]: print(f"   {v/max(tot,1)*100:5.1f}%  {o}")

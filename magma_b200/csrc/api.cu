@@ -6,7 +6,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "common.cuh"
+#include "lu_common.cuh"
 
 using namespace mb200;
 
@@ -95,8 +95,14 @@ magma_int_t magma_dgetrf_batched(magma_int_t m, magma_int_t n, double **dA_array
         if (m <= 32 && n <= 32 && g_tier != 2)
             rc = lu_small_launch(d, m, n, dA_array + off, ipiv_array + off, info_array + off, 0, nullptr, 0, cnt,
                                  nullptr, s);
-        if (rc == -100)
-            rc = lu_blocked_launch(d, m, n, dA_array + off, ipiv_array + off, info_array + off, cnt, nullptr, s);
+        if (rc == -100) {
+            void *ws = queue_dscratch(queue, lu_blocked_workspace_bytes(cnt));
+            if (!ws) {
+                magma_xerbla(__func__, -MAGMA_ERR_DEVICE_ALLOC);
+                return MAGMA_ERR_DEVICE_ALLOC;
+            }
+            rc = lu_blocked_launch(d, m, n, dA_array + off, ipiv_array + off, info_array + off, cnt, nullptr, ws, s);
+        }
         if (rc != 0) {
             magma_xerbla(__func__, -rc);
             return rc;
@@ -206,7 +212,8 @@ magma_int_t magma_dgesv_batched(magma_int_t n, magma_int_t nrhs, double **dA_arr
 // ---------------------------------------------------------------------------------------------
 // Variable-size LU. Workspace layout (ints): [ idx_small (batch) | idx_big (batch) | counts (8) ].
 // ---------------------------------------------------------------------------------------------
-static size_t vbatched_work_bytes(long batch) { return (size_t)(2 * batch + 8) * sizeof(int); }
+static size_t vbatched_lists_bytes(long batch) { return (((size_t)(2 * batch + 8) * sizeof(int)) + 511) & ~(size_t)511; }
+static size_t vbatched_work_bytes(long batch) { return vbatched_lists_bytes(batch) + lu_blocked_workspace_bytes(batch); }
 
 static magma_int_t vbatched_run(magma_int_t *m, magma_int_t *n, int max_m, int max_n, double **dA_array,
                                 magma_int_t *ldda, magma_int_t **ipiv_array, magma_int_t *info_array, void *work,
@@ -228,6 +235,7 @@ static magma_int_t vbatched_run(magma_int_t *m, magma_int_t *n, int max_m, int m
     int *idx_small = (int *)work;
     int *idx_big = idx_small + batch;
     int *counts = idx_big + batch;
+    void *recs = (char *)work + vbatched_lists_bytes(batch);
     long ns = known_small, nbig = known_big;
     if (ns < 0) {
         // expert (asynchronous) entry: the bin sizes are unknown on the host and reading them back
@@ -241,9 +249,9 @@ static magma_int_t vbatched_run(magma_int_t *m, magma_int_t *n, int max_m, int m
     if (ns > 0 && g_tier != 2)
         rc = lu_small_launch(d, 32, 32, dA_array, ipiv_array, info_array, 0, nullptr, 0, ns, idx_small, s);
     else if (ns > 0)
-        rc = lu_blocked_launch(d, 32, 32, dA_array, ipiv_array, info_array, ns, idx_small, s);
+        rc = lu_blocked_launch(d, 32, 32, dA_array, ipiv_array, info_array, ns, idx_small, recs, s);
     if (rc != 0) return rc;
-    if (nbig > 0) rc = lu_blocked_launch(d, max_m, max_n, dA_array, ipiv_array, info_array, nbig, idx_big, s);
+    if (nbig > 0) rc = lu_blocked_launch(d, max_m, max_n, dA_array, ipiv_array, info_array, nbig, idx_big, recs, s);
     return rc;
 }
 
@@ -477,7 +485,7 @@ static magma_int_t host_pipeline(bool solve, int m, int n, int nrhs, double *hA,
     long chunk = (long)std::max<size_t>(1, ((size_t)256 << 20) / per_mat);
     if (chunk > batch) chunk = batch;
     const size_t stride = ((per_mat * chunk + 64 + 255) / 256) * 256;
-    char *dev = (char *)queue_dscratch(queue, 2 * stride);
+    char *dev = (char *)queue_dscratch(queue, 2 * stride, 0);
     if (!dev) {
         magma_xerbla(solve ? "magma_b200_dgesv_batched_host" : "magma_b200_dgetrf_batched_host", -MAGMA_ERR_DEVICE_ALLOC);
         return MAGMA_ERR_DEVICE_ALLOC;

@@ -15,8 +15,8 @@ struct magma_queue {
     cudaStream_t stream;
     bool own_stream;
     // lazily grown per-queue scratch (vbatched statistics, host front-end staging)
-    void *dscratch;
-    size_t dscratch_bytes;
+    void *dscratch[2];        // [0] host front-end staging, [1] kernel workspace (pivot records, bins)
+    size_t dscratch_bytes[2];
     void *hscratch;  // pinned
     size_t hscratch_bytes;
     // host front ends: two extra streams + events for the H2D / compute / D2H pipeline
@@ -34,7 +34,7 @@ extern int g_small_rows;  // register tier: rows per lane, 0 = tuned default
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // Scratch accessors (grow-only, never shrink; freed with the queue).
-void *queue_dscratch(magma_queue_t q, size_t bytes);
+void *queue_dscratch(magma_queue_t q, size_t bytes, int slot = 1);
 void *queue_hscratch(magma_queue_t q, size_t bytes);
 
 // Launch error check: the product path fails loudly (no silent fallback).
@@ -86,8 +86,11 @@ magma_int_t lu_small_launch(const Dims &d, int max_m, int max_n, double **dA, in
                             const int *index_list, cudaStream_t s);
 
 // lu_blocked.cu: blocked right-looking LU for any m x n (two kernels per panel step).
+// `workspace` must hold lu_blocked_workspace_bytes(batch) bytes (one 512-byte pivot record per matrix).
+size_t lu_blocked_workspace_bytes(long batch);
 magma_int_t lu_blocked_launch(const Dims &d, int max_m, int max_n, double **dA, int **dipiv,
-                              int *dinfo, long batch, const int *index_list, cudaStream_t s);
+                              int *dinfo, long batch, const int *index_list, void *workspace,
+                              cudaStream_t s);
 
 // getrs.cu
 magma_int_t getrs_launch(int trans, int n, int nrhs, double **dA, int ldda, int **dipiv,

@@ -1,67 +1,53 @@
-// Blocked right-looking LU for any m x n: two kernels per panel step, no scratch memory.
+// Blocked right-looking LU for any m x n: three specialised kernels per 32-column panel step.
 //
 // Replaces the reference's host recursion (src/zgetrf_batched.cpp:149-203 ->
 // src/zgetrf_panel_batched.cpp:101-196 -> src/zgetf2_batched.cpp:95-287), which issues 42/105/231
 // launches per call at n = 128/256/512: fused panel, setup_pivinfo, adjust_ipiv, 2x laswp,
 // recursive trsm, cublasDgemmBatched (+3 pointer-displacement kernels each). Here a step is
 //   panel_kernel  : one CTA per matrix, panel rows in registers (thread = R rows x W columns),
-//                   CREDUX + shared-memory two-level pivot search, lazy row interchanges,
-//                   writes the factored panel in final row order and ipiv (global indices);
-//   update_kernel : one CTA per (matrix, 64-column tile). Rebuilds the step's net row
-//                   permutation from ipiv in one warp, applies it to the tile (left tiles: swap
-//                   only), solves the W x 64 block row against the unit-lower L11, and applies
-//                   the rank-W update to every row below, accumulating in place with one fma
-//                   per k in increasing k (bit-identical to oracle/lu_oracle.c).
-// so n = 128/256/512 take 8/16/32 launches, and pivinfo/adjust/displace kernels do not exist.
-#include "common.cuh"
+//                   CREDUX + shared-memory two-level pivot search, lazy row interchanges; writes
+//                   the factored panel in final row order, ipiv (global indices) and the step's
+//                   net row permutation (which rows land in the top block, which top rows go
+//                   down) into a 512-byte per-matrix record -- the threads know it from their
+//                   final positions, there is no setup_pivinfo / adjust_ipiv pass;
+//   swap_trsm_kernel : one CTA per (matrix, 64-column tile): applies the permutation to the tile
+//                   (left tiles: interchanges only), and for tiles right of the panel solves the
+//                   W x 64 block row against the unit-lower L11 and stores U12;
+//   gemm_kernel   : C(r,c) = fma(-L21(r,k), U12(k,c), C(r,c)), k increasing, one 128x64 tile per
+//                   CTA (4x8 register tiles, operands staged once in shared memory).
+// All arithmetic is in the canonical order of oracle/lu_oracle.c: bit-identical factors.
+#include "lu_common.cuh"
 
 namespace mb200 {
 
 namespace {
 
-// -------------------------------------------------------------------------------------------
-// (bits, pos) arg-max over a warp: larger |x| bit pattern wins, ties go to the smaller pos.
-// Every lane returns the winner's values.
-// -------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_argmax(unsigned long long bits, int pos,
-                                            unsigned long long &wbits, int &wpos)
-{
-    const unsigned full = 0xffffffffu;
-    const unsigned hi = (unsigned)(bits >> 32);
-    const unsigned mx = __reduce_max_sync(full, hi);
-    bool cand = (hi == mx);
-    unsigned bal = __ballot_sync(full, cand);
-    if (__popc(bal) != 1) {
-        const unsigned lo = cand ? (unsigned)bits : 0u;
-        const unsigned mx2 = __reduce_max_sync(full, lo);
-        cand = cand && (lo == mx2);
-        bal = __ballot_sync(full, cand);
-        if (__popc(bal) != 1) {
-            const unsigned kp = cand ? (unsigned)pos : 0xffffffffu;
-            const unsigned mp = __reduce_min_sync(full, kp);
-            cand = cand && ((unsigned)pos == mp);
-            bal = __ballot_sync(full, cand);
-        }
-    }
-    const int wl = __ffs(bal) - 1;
-    wbits = __shfl_sync(full, bits, wl);
-    wpos = __shfl_sync(full, pos, wl);
-}
+constexpr int NOPOS = NOPOS_I;
+constexpr int KB = 32;  // widest panel
 
-constexpr int NOPOS = 0x7fffffff;
+// Per-matrix, per-step record written by the panel kernel, read by swap_trsm_kernel.
+struct PivRec {
+    int top_src[KB];   // original (panel-relative) row that ends at top position p
+    int down_dst[KB];  // positions >= jb that receive an original top row ...
+    int down_src[KB];  // ... and which one
+    int n_down;
+    int pad[31];
+};
+static_assert(sizeof(PivRec) == 512, "PivRec layout");
 
 // -------------------------------------------------------------------------------------------
 // Panel factorisation, registers. Thread t owns panel rows t, t+T, ... (R of them), W columns.
 // -------------------------------------------------------------------------------------------
 template <int R, int W>
 __global__ void __launch_bounds__(512)
-panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__restrict__ dinfo, int j,
-             long batch, const int *__restrict__ index_list)
+panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__restrict__ dinfo,
+             PivRec *__restrict__ recs, int j, long batch, const int *__restrict__ index_list)
 {
     __shared__ unsigned long long cbits[2][32];
     __shared__ int cpos[2][32];
-    __shared__ __align__(16) double prow[2][W];
+    __shared__ __align__(16) double prow[2][W + 2];  // [W] = 1/pivot
     __shared__ int sipiv[W];
+    __shared__ int s_ndown;
 
     const long slot = blockIdx.x;
     const long b = index_list ? index_list[slot] : slot;
@@ -76,6 +62,7 @@ panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__
     const int tid = threadIdx.x;
     const int lane = tid & 31, wid = tid >> 5, nw = T >> 5;
     double *__restrict__ A = dA[b] + (size_t)j + (size_t)j * ld;  // panel origin
+    PivRec &rec = recs[slot];
 
     double a[R][W];
     int pos[R];
@@ -84,8 +71,9 @@ panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__
         const int r = tid + k * T;
         pos[k] = (r < mp) ? r : NOPOS;
 #pragma unroll
-        for (int c = 0; c < W; ++c) a[k][c] = (r < mp && c < jb) ? A[r + (size_t)c * ld] : 0.0;
+        for (int c = 0; c < W; ++c) a[k][c] = (r < mp && c < jb) ? A[r + (size_t)c * ld] : 1.0;
     }
+    if (tid == 0) s_ndown = 0;
     int info = 0;
 
 #pragma unroll
@@ -94,16 +82,25 @@ panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__
             // local best over this thread's rows
             unsigned long long lb = 0;
             int lp = NOPOS;
+            int lk = 0;
 #pragma unroll
             for (int k = 0; k < R; ++k) {
                 const bool act = (pos[k] >= i) && (pos[k] != NOPOS);
                 const unsigned long long v =
                     (unsigned long long)__double_as_longlong(a[k][i]) & 0x7fffffffffffffffull;
-                if (act && (v > lb || (v == lb && pos[k] < lp))) {
+                if (act && (v > lb || lp == NOPOS || (v == lb && pos[k] < lp))) {
                     lb = v;
                     lp = pos[k];
+                    lk = k;
                 }
             }
+            // every thread prepares the reciprocal of its own candidate while the search runs
+            double cv = a[0][i];
+#pragma unroll
+            for (int k = 1; k < R; ++k)
+                if (lk == k) cv = a[k][i];
+            const double rinv = 1.0 / cv;
+
             unsigned long long wb;
             int wp;
             warp_argmax(lb, lp, wb, wp);
@@ -119,21 +116,27 @@ panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__
             }
             const int ppos = wp;  // panel-relative position of the pivot row (>= i)
             if (tid == 0) sipiv[i] = ppos;
+            if (lp == ppos) {
+                // this thread owns the pivot row (its local winner): publish row and reciprocal
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    if (lk == k) {
+#pragma unroll
+                        for (int c = 0; c < W; ++c)
+                            if (c >= i) prow[i & 1][c] = a[k][c];
+                    }
+                }
+                prow[i & 1][W] = rinv;
+            }
 #pragma unroll
             for (int k = 0; k < R; ++k) {
-                if (pos[k] == ppos) {
-                    pos[k] = i;
-#pragma unroll
-                    for (int c = 0; c < W; ++c)
-                        if (c >= i) prow[i & 1][c] = a[k][c];
-                } else if (pos[k] == i) {
-                    pos[k] = ppos;
-                }
+                if (pos[k] == ppos) pos[k] = i;
+                else if (pos[k] == i) pos[k] = ppos;
             }
             __syncthreads();
             const double piv = prow[i & 1][i];
             if (piv != 0.0) {
-                const double r = 1.0 / piv;
+                const double r = prow[i & 1][W];
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
                     if (pos[k] > i && pos[k] != NOPOS) {
@@ -150,36 +153,49 @@ panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__
         }
     }
 
-    // factored panel, rows in final order
+    // factored panel, rows in final order; permutation record
 #pragma unroll
     for (int k = 0; k < R; ++k) {
         if (pos[k] != NOPOS) {
 #pragma unroll
             for (int c = 0; c < W; ++c)
                 if (c < jb) A[pos[k] + (size_t)c * ld] = a[k][c];
+            const int orig = tid + k * T;
+            if (pos[k] < jb) {
+                rec.top_src[pos[k]] = orig;
+            } else if (pos[k] != orig) {  // an original top row that went down
+                const int e = atomicAdd(&s_ndown, 1);
+                rec.down_dst[e] = pos[k];
+                rec.down_src[e] = orig;
+            }
         }
     }
     if (tid < jb) dipiv[b][j + tid] = j + sipiv[tid] + 1;
+    __syncthreads();
     if (tid == 0) {
-        if (j == 0) dinfo[b] = info ? info : 0;
+        rec.n_down = s_ndown;
+        if (j == 0) dinfo[b] = info;
         else if (info && dinfo[b] == 0) dinfo[b] = j + info;
     }
 }
 
 // -------------------------------------------------------------------------------------------
 // Panel factorisation straight on global memory: correctness fallback for panels taller than
-// the register kernel covers (m - j > 8192). One CTA per matrix, W columns.
+// the register kernel covers (m - j > 8192). One CTA per matrix, W columns. Interchanges are
+// physical here, so the record lists are rebuilt from the pivots by thread 0.
 // -------------------------------------------------------------------------------------------
 template <int W>
 __global__ void __launch_bounds__(256)
-panel_global_kernel(Dims d, double **dA, int **dipiv, int *dinfo, int j, long batch, const int *index_list)
+panel_global_kernel(Dims d, double **dA, int **dipiv, int *dinfo, PivRec *recs, int j, long batch,
+                    const int *index_list)
 {
     __shared__ unsigned long long cbits[8];
     __shared__ int cpos[8];
     __shared__ int spiv;
+    __shared__ int lp_[W];
     const long slot = blockIdx.x;
     const long b = index_list ? index_list[slot] : slot;
-    if (b < 0) return;  // unused tail of a vbatched index list
+    if (b < 0) return;
     int m, n, ld;
     dims_of(d, b, m, n, ld);
     const int mn = m < n ? m : n;
@@ -216,7 +232,10 @@ panel_global_kernel(Dims d, double **dA, int **dipiv, int *dinfo, int j, long ba
         }
         __syncthreads();
         const int p = spiv;
-        if (tid == 0) dipiv[b][j + i] = j + p + 1;
+        if (tid == 0) {
+            dipiv[b][j + i] = j + p + 1;
+            lp_[i] = p;
+        }
         if (p != i && tid < jb) {
             const double t0 = A[i + (size_t)tid * ld];
             A[i + (size_t)tid * ld] = A[p + (size_t)tid * ld];
@@ -238,50 +257,69 @@ panel_global_kernel(Dims d, double **dA, int **dipiv, int *dinfo, int j, long ba
         __syncthreads();
     }
     if (tid == 0) {
+        // net permutation of the jb sequential interchanges (tiny: jb <= 8 here)
+        PivRec &rec = recs[slot];
+        int top[W], epos[W], econt[W], ne = 0;
+        for (int k = 0; k < jb; ++k) top[k] = k;
+        for (int i = 0; i < jb; ++i) {
+            const int p = lp_[i];
+            if (p == i) continue;
+            if (p < jb) {
+                const int t = top[i];
+                top[i] = top[p];
+                top[p] = t;
+                continue;
+            }
+            int e = -1;
+            for (int q = 0; q < ne; ++q)
+                if (epos[q] == p) e = q;
+            if (e < 0) {
+                e = ne++;
+                epos[e] = p;
+                econt[e] = p;
+            }
+            const int t = top[i];
+            top[i] = econt[e];
+            econt[e] = t;
+        }
+        for (int k = 0; k < jb; ++k) rec.top_src[k] = top[k];
+        for (int e = 0; e < ne; ++e) {
+            rec.down_dst[e] = epos[e];
+            rec.down_src[e] = econt[e];
+        }
+        rec.n_down = ne;
         if (j == 0) dinfo[b] = info;
         else if (info && dinfo[b] == 0) dinfo[b] = j + info;
     }
 }
 
 // -------------------------------------------------------------------------------------------
-// Update kernel.
+// Interchanges on a 64-column tile (+ U12 = L11^-1 * block row for tiles right of the panel).
 // -------------------------------------------------------------------------------------------
-constexpr int TN = 64;    // columns per CTA
-constexpr int TM = 128;   // rows per GEMM chunk
-constexpr int KB = 32;    // max panel width
-constexpr int UPD_THREADS = 256;
-
-struct UpdSmem {
-    double As[KB * TM];       // L21 chunk, k-major: As[k*TM + r]      (aliases T0/E0 staging)
-    double Bs[KB * TN];       // U12 tile,  k-major: Bs[k*TN + c]
-    double Ls[KB * (KB + 1)]; // L11, Ls[i*(KB+1) + k]
-    int top_src[KB];          // original (panel-relative) row now at top position k
-    int top_ext[KB];          // if top_src[k] >= jb: index of that row in the extra list
-    int ext_pos[KB];          // extra positions (panel-relative, >= jb)
-    int ext_src[KB];          // original top row (< jb) that ends at ext_pos[e]
-    int n_ext;
-};
+constexpr int TN = 64;
+constexpr int ST_THREADS = 128;
+constexpr int TNP = TN + 1;
 
 template <int W>
-__global__ void __launch_bounds__(UPD_THREADS, 2)
-update_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int j, int right_tiles,
-              int left_tiles, long batch, const int *__restrict__ index_list)
+__global__ void __launch_bounds__(ST_THREADS)
+swap_trsm_kernel(Dims d, double **__restrict__ dA, const PivRec *__restrict__ recs, int j, int right_tiles,
+                 int left_tiles, long batch, const int *__restrict__ index_list)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    UpdSmem &S = *reinterpret_cast<UpdSmem *>(smem_raw);
+    __shared__ double T0[KB * TNP];       // original top rows   [k*TNP + c]
+    __shared__ double Bs[KB * TNP];       // permuted top block  [p*TNP + c]
+    __shared__ double Ls[KB * (KB + 1)];  // L11                 [i*(KB+1) + k]
+    __shared__ int s_top[KB], s_ddst[KB], s_dsrc[KB];
 
     const int tiles = right_tiles + left_tiles;
     const long slot = blockIdx.x / tiles;
     const int tile = blockIdx.x % tiles;
     const long b = index_list ? index_list[slot] : slot;
-    if (b < 0) return;  // unused tail of a vbatched index list
+    if (b < 0) return;
     int m, n, ld;
     dims_of(d, b, m, n, ld);
     const int mn = m < n ? m : n;
     if (j >= mn) return;
     const int jb = (mn - j) < W ? (mn - j) : W;
-
-    // column range of this tile
     int c0, c1;
     bool right;
     if (tile < right_tiles) {
@@ -295,107 +333,299 @@ update_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int j,
     }
     if (c0 >= c1) return;
     const int wt = c1 - c0;
-
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double *__restrict__ A = dA[b];
-    const int *__restrict__ ipiv = dipiv[b] + j;
-
-    // ---- 1. net permutation of this step's interchanges (warp 0) ------------------------------
-    if (wid == 0) {
-        const unsigned full = 0xffffffffu;
-        int cur_top = lane;           // content of top position `lane`
-        int epos = -1, econt = -1;    // extra list lives in lanes 0..ne-1
-        int ne = 0;
-        const int myp = (lane < jb) ? (ipiv[lane] - 1 - j) : 0;
-        for (int i = 0; i < jb; ++i) {
-            const int p = __shfl_sync(full, myp, i);
-            if (p == i) continue;
-            const int ci = __shfl_sync(full, cur_top, i);
-            if (p < jb) {
-                const int cp = __shfl_sync(full, cur_top, p);
-                if (lane == i) cur_top = cp;
-                if (lane == p) cur_top = ci;
-            } else {
-                const unsigned hit = __ballot_sync(full, lane < ne && epos == p);
-                if (hit) {
-                    const int e = __ffs(hit) - 1;
-                    const int ce = __shfl_sync(full, econt, e);
-                    if (lane == i) cur_top = ce;
-                    if (lane == e) econt = ci;
-                } else {
-                    if (lane == i) cur_top = p;
-                    if (lane == ne) { epos = p; econt = ci; }
-                    ++ne;
-                }
-            }
+    double *Ap = A + (size_t)j;  // row origin of the panel
+    const PivRec &rec = recs[slot];
+    if (tid < KB) {
+        s_top[tid] = rec.top_src[tid];
+        s_ddst[tid] = rec.down_dst[tid];
+        s_dsrc[tid] = rec.down_src[tid];
+    }
+    const int nd = rec.n_down;
+    // original top rows (coalesced: k is the fast index)
+#pragma unroll 4
+    for (int idx = tid; idx < KB * TN; idx += ST_THREADS) {
+        const int k = idx & 31, c = idx >> 5;
+        if (k < jb && c < wt) T0[k * TNP + c] = Ap[k + (size_t)(c0 + c) * ld];
+    }
+    if (right) {
+        for (int idx = tid; idx < KB * KB; idx += ST_THREADS) {
+            const int i = idx & 31, k = idx >> 5;
+            if (i < jb && k < jb) Ls[i * (KB + 1) + k] = Ap[i + (size_t)(j + k) * ld];
         }
-        // map top rows that came from below to their slot in the extra list
-        int te = -1;
-        for (int e = 0; e < ne; ++e) {
-            const int pe = __shfl_sync(full, epos, e);
-            if (cur_top == pe) te = e;
-        }
-        if (lane < KB) {
-            S.top_src[lane] = cur_top;
-            S.top_ext[lane] = te;
-            S.ext_pos[lane] = epos;
-            S.ext_src[lane] = econt;
-        }
-        if (lane == 0) S.n_ext = ne;
     }
     __syncthreads();
-    const int ne = S.n_ext;
-
-    // ---- 2. apply it to this tile's columns ---------------------------------------------------
-    // T0 = original top rows, E0 = original extra rows (staged in As)
-    double *T0 = S.As;            // [k*TN + c]
-    double *E0 = S.As + KB * TN;  // [e*TN + c]
-    double *Ap = A + (size_t)j;   // row origin of the panel
-    for (int idx = tid; idx < jb * wt; idx += UPD_THREADS) {
-        const int k = idx % jb, c = idx / jb;
-        T0[k * TN + c] = Ap[k + (size_t)(c0 + c) * ld];
-    }
-    for (int idx = tid; idx < ne * wt; idx += UPD_THREADS) {
-        const int e = idx % ne, c = idx / ne;
-        E0[e * TN + c] = Ap[S.ext_pos[e] + (size_t)(c0 + c) * ld];
+    // permuted top block: rows that come up from below are read before their slots are overwritten
+#pragma unroll 4
+    for (int idx = tid; idx < KB * TN; idx += ST_THREADS) {
+        const int c = idx & 63, p = idx >> 6;
+        if (p < jb && c < wt) {
+            const int src = s_top[p];
+            Bs[p * TNP + c] = (src < jb) ? T0[src * TNP + c] : Ap[src + (size_t)(c0 + c) * ld];
+        }
     }
     __syncthreads();
-    for (int idx = tid; idx < ne * wt; idx += UPD_THREADS) {
-        const int e = idx % ne, c = idx / ne;
-        Ap[S.ext_pos[e] + (size_t)(c0 + c) * ld] = T0[S.ext_src[e] * TN + c];
+    if (lane < nd) {
+        const int dst = s_ddst[lane], src = s_dsrc[lane];
+        for (int c = wid; c < wt; c += ST_THREADS / 32) Ap[dst + (size_t)(c0 + c) * ld] = T0[src * TNP + c];
     }
     if (!right) {
-        for (int idx = tid; idx < jb * wt; idx += UPD_THREADS) {
-            const int k = idx % jb, c = idx / jb;
-            const int src = S.top_src[k];
-            if (src != k) {
-                const double v = (src < jb) ? T0[src * TN + c] : E0[S.top_ext[k] * TN + c];
-                Ap[k + (size_t)(c0 + c) * ld] = v;
-            }
+#pragma unroll 4
+        for (int idx = tid; idx < KB * TN; idx += ST_THREADS) {
+            const int k = idx & 31, c = idx >> 5;
+            if (k < jb && c < wt && s_top[k] != k) Ap[k + (size_t)(c0 + c) * ld] = Bs[k * TNP + c];
         }
         return;
     }
-    for (int idx = tid; idx < KB * TN; idx += UPD_THREADS) {
-        const int k = idx / TN, c = idx % TN;
-        double v = 0.0;
-        if (k < jb && c < wt) {
-            const int src = S.top_src[k];
-            v = (src < jb) ? T0[src * TN + c] : E0[S.top_ext[k] * TN + c];
-        }
-        S.Bs[k * TN + c] = v;
-    }
-    // L11 (unit lower) -> shared
-    for (int idx = tid; idx < jb * jb; idx += UPD_THREADS) {
-        const int i = idx % jb, k = idx / jb;
-        S.Ls[i * (KB + 1) + k] = Ap[i + (size_t)(j + k) * ld];
-    }
-    __syncthreads();
-
-    // ---- 3. U12 = L11^-1 * top block: one thread per column, canonical order --------------------
+    // U12 = L11^-1 * Bs: one thread per column, canonical order
     if (tid < wt) {
         double x[W];
 #pragma unroll
-        for (int i = 0; i < W; ++i) x[i] = S.Bs[i * TN + tid];
+        for (int i = 0; i < W; ++i) x[i] = (i < jb) ? Bs[i * TNP + tid] : 0.0;
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            if (k < jb) {
+#pragma unroll
+                for (int i = 0; i < W; ++i)
+                    if (i > k && i < jb) x[i] = fma(-Ls[i * (KB + 1) + k], x[k], x[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < W; ++i)
+            if (i < jb) Bs[i * TNP + tid] = x[i];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int idx = tid; idx < KB * TN; idx += ST_THREADS) {
+        const int k = idx & 31, c = idx >> 5;
+        if (k < jb && c < wt) Ap[k + (size_t)(c0 + c) * ld] = Bs[k * TNP + c];
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// Trailing update: one 128 x 64 tile of C per CTA.
+// -------------------------------------------------------------------------------------------
+constexpr int GM = 128, GN = 64, GEMM_THREADS = 256;
+
+template <int W>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_kernel(Dims d, double **__restrict__ dA, int j, int tiles_m, int tiles_n, long batch,
+            const int *__restrict__ index_list)
+{
+    __shared__ __align__(16) double As[W * GM];  // [k*GM + r]
+    __shared__ __align__(16) double Bs[W * GN];  // [k*GN + c]
+
+    const int tiles = tiles_m * tiles_n;
+    const long slot = blockIdx.x / tiles;
+    const int t = blockIdx.x % tiles;
+    const long b = index_list ? index_list[slot] : slot;
+    if (b < 0) return;
+    int m, n, ld;
+    dims_of(d, b, m, n, ld);
+    const int mn = m < n ? m : n;
+    if (j >= mn) return;
+    const int jb = (mn - j) < W ? (mn - j) : W;
+    const int r0 = j + jb + (t % tiles_m) * GM;
+    const int c0 = j + jb + (t / tiles_m) * GN;
+    if (r0 >= m || c0 >= n) return;
+    const int rows = (m - r0) < GM ? (m - r0) : GM;
+    const int cols = (n - c0) < GN ? (n - c0) : GN;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double *__restrict__ A = dA[b];
+    const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+
+    // warp grid 4 x 2 over the tile; lane grid 8 x 4; thread tile 4 rows x 8 cols:
+    // rows {2lr, 2lr+1, 16+2lr, 17+2lr}, cols {8q + 2lc, 8q + 2lc + 1 : q = 0..3} of the warp tile
+    const int wr = wid & 3, wc = wid >> 2;
+    const int lr = lane & 7, lc = lane >> 3;
+    const int trow = wr * 32 + 2 * lr;
+    const int tcol = wc * 32 + 2 * lc;
+
+    // C first (longest latency), then the operands
+    double acc[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = tcol + 8 * q + cc;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = trow + 16 * h;
+                double v0 = 0.0, v1 = 0.0;
+                if (c < cols && r < rows) {
+                    const double *src = A + (size_t)(r0 + r) + (size_t)(c0 + c) * ld;
+                    if (vec_ok && ((r0 + r) & 1) == 0 && r + 1 < rows) {
+                        const double2 t2 = *reinterpret_cast<const double2 *>(src);
+                        v0 = t2.x;
+                        v1 = t2.y;
+                    } else {
+                        v0 = src[0];
+                        if (r + 1 < rows) v1 = src[1];
+                    }
+                }
+                acc[2 * h][2 * q + cc] = v0;
+                acc[2 * h + 1][2 * q + cc] = v1;
+            }
+        }
+    const double *__restrict__ L21 = A + (size_t)j * ld;  // column j, absolute rows
+    const double *__restrict__ U12 = A + (size_t)j;       // row j, absolute columns
+#pragma unroll 4
+    for (int idx = tid; idx < W * GM; idx += GEMM_THREADS) {
+        const int r = idx & (GM - 1), k = idx / GM;
+        As[idx] = (r < rows && k < jb) ? L21[(size_t)(r0 + r) + (size_t)k * ld] : 0.0;
+    }
+#pragma unroll 4
+    for (int idx = tid; idx < W * GN; idx += GEMM_THREADS) {
+        const int k = idx % W, c = idx / W;  // k fast: contiguous in global memory
+        Bs[k * GN + c] = (c < cols && k < jb) ? U12[(size_t)k + (size_t)(c0 + c) * ld] : 0.0;
+    }
+    __syncthreads();
+
+#pragma unroll 4
+    for (int k = 0; k < W; ++k) {
+        if (k < jb) {
+            const double2 a01 = *reinterpret_cast<const double2 *>(&As[k * GM + trow]);
+            const double2 a23 = *reinterpret_cast<const double2 *>(&As[k * GM + trow + 16]);
+            const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double2 bq = *reinterpret_cast<const double2 *>(&Bs[k * GN + tcol + 8 * q]);
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    acc[rr][2 * q] = fma(-av[rr], bq.x, acc[rr][2 * q]);
+                    acc[rr][2 * q + 1] = fma(-av[rr], bq.y, acc[rr][2 * q + 1]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = tcol + 8 * q + cc;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = trow + 16 * h;
+                if (c < cols && r < rows) {
+                    double *dst = A + (size_t)(r0 + r) + (size_t)(c0 + c) * ld;
+                    if (vec_ok && ((r0 + r) & 1) == 0 && r + 1 < rows) {
+                        *reinterpret_cast<double2 *>(dst) =
+                            make_double2(acc[2 * h][2 * q + cc], acc[2 * h + 1][2 * q + cc]);
+                    } else {
+                        dst[0] = acc[2 * h][2 * q + cc];
+                        if (r + 1 < rows) dst[1] = acc[2 * h + 1][2 * q + cc];
+                    }
+                }
+            }
+        }
+}
+
+
+// -------------------------------------------------------------------------------------------
+// Strip-resident update (panels at most 128 rows tall): one CTA per (matrix, 64-column strip).
+// The whole strip -- block row and every row below it -- is brought into shared memory with
+// coalesced full-column loads, the step's interchanges are applied there (no 8-byte scattered
+// global accesses, no partial-sector traffic), the block row is solved against L11, the rows
+// below get their rank-W update from shared memory, and the strip goes back with coalesced stores:
+// HBM sees exactly one read and one write of the trailing matrix per step.
+// -------------------------------------------------------------------------------------------
+constexpr int SW = 64;            // strip width
+constexpr int SROWS = 128;        // tallest strip
+constexpr int LDC = SROWS + 2;    // padded column stride of the strip buffer (even: 16-byte rows pairs)
+constexpr int STRIP_THREADS = 256;
+
+struct StripSmem {
+    double Cs[SW * LDC];        // strip, column-major: Cs[c*LDC + r], r = 0 is panel row j
+    double As[KB * SROWS];      // L21, k-major: As[k*SROWS + r], r = 0 is row j + jb
+    double Ls[KB * (KB + 1)];   // L11
+    int top[KB], ddst[KB], dsrc[KB];
+};
+
+template <int W>
+__global__ void __launch_bounds__(STRIP_THREADS, 2)
+update_strip_kernel(Dims d, double **__restrict__ dA, const PivRec *__restrict__ recs, int j, int strips,
+                    long batch, const int *__restrict__ index_list)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StripSmem &S = *reinterpret_cast<StripSmem *>(smem_raw);
+
+    const long slot = blockIdx.x / strips;
+    const int strip = blockIdx.x % strips;
+    const long b = index_list ? index_list[slot] : slot;
+    if (b < 0) return;
+    int m, n, ld;
+    dims_of(d, b, m, n, ld);
+    const int mn = m < n ? m : n;
+    if (j >= mn) return;
+    const int jb = (mn - j) < W ? (mn - j) : W;
+    const int c0 = j + jb + strip * SW;
+    if (c0 >= n) return;
+    const int wt = (n - c0) < SW ? (n - c0) : SW;
+    const int mp = m - j;        // strip rows (<= SROWS)
+    const int mr = mp - jb;      // rows below the block row
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double *__restrict__ A = dA[b];
+    const PivRec &rec = recs[slot];
+    if (tid < KB) {
+        S.top[tid] = rec.top_src[tid];
+        S.ddst[tid] = rec.down_dst[tid];
+        S.dsrc[tid] = rec.down_src[tid];
+    }
+    const int nd = rec.n_down;
+
+    // ---- loads: strip (full columns), L11, L21 ------------------------------------------------
+    for (int c = wid; c < wt; c += STRIP_THREADS / 32) {
+        const double *col = A + (size_t)j + (size_t)(c0 + c) * ld;
+#pragma unroll
+        for (int r = lane; r < SROWS; r += 32)
+            if (r < mp) S.Cs[c * LDC + r] = col[r];
+    }
+    for (int idx = tid; idx < KB * KB; idx += STRIP_THREADS) {
+        const int i = idx & 31, k = idx >> 5;
+        if (i < jb && k < jb) S.Ls[i * (KB + 1) + k] = A[(size_t)(j + i) + (size_t)(j + k) * ld];
+    }
+#pragma unroll 4
+    for (int idx = tid; idx < KB * SROWS; idx += STRIP_THREADS) {
+        const int r = idx & (SROWS - 1), k = idx >> 7;
+        S.As[idx] = (r < mr && k < jb) ? A[(size_t)(j + jb + r) + (size_t)(j + k) * ld] : 0.0;
+    }
+    __syncthreads();
+
+    // ---- interchanges in shared memory: gather into registers, barrier, scatter ------------------
+    {
+        // items: (p, c) for the jb top positions, then (e, c) for the nd rows that go down
+        const int items = (jb + nd) * SW;
+        double v[(2 * KB * SW) / STRIP_THREADS];
+#pragma unroll
+        for (int u = 0; u < (2 * KB * SW) / STRIP_THREADS; ++u) {
+            const int idx = tid + u * STRIP_THREADS;
+            const int c = idx & (SW - 1), q = idx >> 6;
+            v[u] = 0.0;
+            if (idx < items && c < wt) {
+                const int src = (q < jb) ? S.top[q] : S.dsrc[q - jb];
+                v[u] = S.Cs[c * LDC + src];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < (2 * KB * SW) / STRIP_THREADS; ++u) {
+            const int idx = tid + u * STRIP_THREADS;
+            const int c = idx & (SW - 1), q = idx >> 6;
+            if (idx < items && c < wt) {
+                const int dst = (q < jb) ? q : S.ddst[q - jb];
+                S.Cs[c * LDC + dst] = v[u];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- U12 = L11^-1 * block row: one thread per column, canonical order -------------------------
+    if (tid < wt) {
+        double x[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) x[i] = (i < jb) ? S.Cs[tid * LDC + i] : 0.0;
 #pragma unroll
         for (int k = 0; k < W; ++k) {
             if (k < jb) {
@@ -405,171 +635,249 @@ update_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int j,
             }
         }
 #pragma unroll
-        for (int i = 0; i < W; ++i) {
-            if (i < jb) {
-                S.Bs[i * TN + tid] = x[i];
-                Ap[i + (size_t)(c0 + tid) * ld] = x[i];
-            }
-        }
+        for (int i = 0; i < W; ++i)
+            if (i < jb) S.Cs[tid * LDC + i] = x[i];
     }
     __syncthreads();
 
-    // ---- 4. rows below: C(r, c) = fma(-L21(r,k), U12(k,c), C(r,c)), k increasing ------------------
-    const int r_begin = j + jb;
-    if (r_begin >= m) return;
-    // warp grid 4 x 2 over a 128 x 64 CTA tile; lane grid 8 x 4; thread tile 4 rows x 8 cols:
-    // rows {2lr, 2lr+1, 16+2lr, 17+2lr}, cols {8q + 2lc, 8q + 2lc + 1 : q = 0..3} of the warp tile.
-    const int wr = wid & 3, wc = wid >> 2;
-    const int lr = lane & 7, lc = lane >> 3;
-    const int trow = wr * 32 + 2 * lr;   // + {0,1,16,17}
-    const int tcol = wc * 32 + 2 * lc;   // + 8q + {0,1}
-    const double *__restrict__ L21 = A + (size_t)j * ld;  // column j, absolute rows
-    const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-
-    for (int r0 = r_begin; r0 < m; r0 += TM) {
-        __syncthreads();  // previous chunk's As (or the T0/E0 staging) no longer needed
-        const int rows = (m - r0) < TM ? (m - r0) : TM;
-        for (int idx = tid; idx < KB * TM; idx += UPD_THREADS) {
-            const int r = idx % TM, k = idx / TM;
-            S.As[k * TM + r] = (r < rows && k < jb) ? L21[(size_t)(r0 + r) + (size_t)k * ld] : 0.0;
+    // ---- rows below: C(r,c) = fma(-L21(r,k), U12(k,c), C(r,c)), k increasing ------------------------
+    if (mr > 0) {
+        const int wr = wid & 3, wc = wid >> 2;
+        const int lr = lane & 7, lc = lane >> 3;
+        const int trow = wr * 32 + 2 * lr;   // + {0,1,16,17}, relative to row j + jb
+        const int tcol = wc * 32 + 2 * lc;   // + 8q + {0,1}
+        if (wr * 32 < mr && wc * 32 < wt) {
+            double acc[4][8];
+            // jb may be odd on a matrix's last panel: C rows start at Cs row jb
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const double *colp = &S.Cs[(tcol + 8 * q + cc) * LDC + jb];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = trow + 16 * h;
+                        acc[2 * h][2 * q + cc] = (r < mr) ? colp[r] : 0.0;
+                        acc[2 * h + 1][2 * q + cc] = (r + 1 < mr) ? colp[r + 1] : 0.0;
+                    }
+                }
+#pragma unroll 4
+            for (int k = 0; k < W; ++k) {
+                if (k < jb) {
+                    const double2 a01 = *reinterpret_cast<const double2 *>(&S.As[k * SROWS + trow]);
+                    const double2 a23 = *reinterpret_cast<const double2 *>(&S.As[k * SROWS + trow + 16]);
+                    const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        // U12(k, c) sits in the strip's block row: Cs[c*LDC + k]
+                        const double bx = S.Cs[(tcol + 8 * q) * LDC + k];
+                        const double by = S.Cs[(tcol + 8 * q + 1) * LDC + k];
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) {
+                            acc[rr][2 * q] = fma(-av[rr], bx, acc[rr][2 * q]);
+                            acc[rr][2 * q + 1] = fma(-av[rr], by, acc[rr][2 * q + 1]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    double *colp = &S.Cs[(tcol + 8 * q + cc) * LDC + jb];
+                    const bool cok = (tcol + 8 * q + cc) < wt;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = trow + 16 * h;
+                        if (cok && r < mr) colp[r] = acc[2 * h][2 * q + cc];
+                        if (cok && r + 1 < mr) colp[r + 1] = acc[2 * h + 1][2 * q + cc];
+                    }
+                }
         }
         __syncthreads();
+    }
 
-        double acc[4][8];
-        // load C
+    // ---- store the strip ---------------------------------------------------------------------------
+    for (int c = wid; c < wt; c += STRIP_THREADS / 32) {
+        double *col = A + (size_t)j + (size_t)(c0 + c) * ld;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int c = tcol + 8 * q + cc;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int r = trow + 16 * h;
-                    double v0 = 0.0, v1 = 0.0;
-                    if (c < wt && r < rows) {
-                        const double *src = A + (size_t)(r0 + r) + (size_t)(c0 + c) * ld;
-                        if (vec_ok && ((r0 + r) & 1) == 0 && r + 1 < rows) {
-                            const double2 t2 = *reinterpret_cast<const double2 *>(src);
-                            v0 = t2.x;
-                            v1 = t2.y;
-                        } else {
-                            v0 = src[0];
-                            if (r + 1 < rows) v1 = src[1];
-                        }
-                    }
-                    acc[2 * h][2 * q + cc] = v0;
-                    acc[2 * h + 1][2 * q + cc] = v1;
-                }
+        for (int r = lane; r < SROWS; r += 32)
+            if (r < mp) col[r] = S.Cs[c * LDC + r];
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// Deferred interchanges of the L part: column block J (32 columns) receives, in ONE pass at the
+// end, every interchange of the later panels (LAPACK's dlaswp with k1 = 32(J+1)+1 .. min(m,n)).
+// The reference applies them step by step with 8-byte scattered accesses
+// (magmablas/zlaswp_batched.cu:31-43, "swap left" at src/zgetrf_batched.cpp:167-172); one pass
+// reads and writes each column of L once, coalesced, permuting through shared memory.
+// -------------------------------------------------------------------------------------------
+constexpr int LSWP_THREADS = 256;
+constexpr int LSWP_COLS = 4;  // columns staged per round
+
+__global__ void __launch_bounds__(LSWP_THREADS)
+laswp_left_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int blocks, int max_rows, int step,
+                  long batch, const int *__restrict__ index_list)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *perm = reinterpret_cast<int *>(smem_raw);                                   // [max_rows]
+    int *spiv = perm + max_rows;                                                     // [max_rows]
+    double *buf = reinterpret_cast<double *>(spiv + max_rows + (max_rows & 1) * 0);  // [LSWP_COLS][max_rows]
+    buf = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(buf) + 15) & ~(uintptr_t)15);
+
+    const long slot = blockIdx.x / blocks;
+    const int J = blockIdx.x % blocks;
+    const long b = index_list ? index_list[slot] : slot;
+    if (b < 0) return;
+    int m, n, ld;
+    dims_of(d, b, m, n, ld);
+    const int mn = m < n ? m : n;
+    const int r0 = (J + 1) * step;   // first row touched; columns J*step .. r0-1
+    if (r0 >= mn) return;            // no later panel
+    const int rows = m - r0;
+    const int tid = threadIdx.x;
+    double *__restrict__ A = dA[b];
+    const int *__restrict__ ipiv = dipiv[b];
+    for (int i = tid; i < rows; i += LSWP_THREADS) {
+        perm[i] = i;
+        spiv[i] = (r0 + i < mn) ? (ipiv[r0 + i] - 1 - r0) : i;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int kmax = mn - r0;
+        bool any = false;
+        for (int i = 0; i < kmax; ++i) {
+            const int p = spiv[i];
+            if (p != i) {
+                const int t = perm[i];
+                perm[i] = perm[p];
+                perm[p] = t;
+                any = true;
             }
         }
-#pragma unroll 4
-        for (int k = 0; k < W; ++k) {
-            if (k < jb) {
-                const double2 a01 = *reinterpret_cast<const double2 *>(&S.As[k * TM + trow]);
-                const double2 a23 = *reinterpret_cast<const double2 *>(&S.As[k * TM + trow + 16]);
-                const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double2 bq = *reinterpret_cast<const double2 *>(&S.Bs[k * TN + tcol + 8 * q]);
-#pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) {
-                        acc[rr][2 * q] = fma(-av[rr], bq.x, acc[rr][2 * q]);
-                        acc[rr][2 * q + 1] = fma(-av[rr], bq.y, acc[rr][2 * q + 1]);
-                    }
-                }
+        spiv[0] = any ? 1 : 0;
+    }
+    __syncthreads();
+    if (!spiv[0]) return;
+    const int cbeg = J * step, cend = r0;  // r0 <= mn <= n
+    for (int cb = cbeg; cb < cend; cb += LSWP_COLS) {
+        const int nc = (cend - cb) < LSWP_COLS ? (cend - cb) : LSWP_COLS;
+        for (int c = 0; c < nc; ++c) {
+            const double *col = A + (size_t)r0 + (size_t)(cb + c) * ld;
+            for (int i = tid; i < rows; i += LSWP_THREADS) buf[c * max_rows + i] = col[i];
+        }
+        __syncthreads();
+        for (int c = 0; c < nc; ++c) {
+            double *col = A + (size_t)r0 + (size_t)(cb + c) * ld;
+            for (int i = tid; i < rows; i += LSWP_THREADS) {
+                const int src = perm[i];
+                if (src != i) col[i] = buf[c * max_rows + src];
             }
         }
-        // store C
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                const int c = tcol + 8 * q + cc;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int r = trow + 16 * h;
-                    if (c < wt && r < rows) {
-                        double *dst = A + (size_t)(r0 + r) + (size_t)(c0 + c) * ld;
-                        if (vec_ok && ((r0 + r) & 1) == 0 && r + 1 < rows) {
-                            *reinterpret_cast<double2 *>(dst) =
-                                make_double2(acc[2 * h][2 * q + cc], acc[2 * h + 1][2 * q + cc]);
-                        } else {
-                            dst[0] = acc[2 * h][2 * q + cc];
-                            if (r + 1 < rows) dst[1] = acc[2 * h + 1][2 * q + cc];
-                        }
-                    }
-                }
-            }
-        }
+        __syncthreads();
     }
 }
 
 template <int R, int W>
-magma_int_t run_step(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo, int j,
-                     long batch, const int *il, cudaStream_t s, bool global_panel)
+magma_int_t run_step(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo, PivRec *recs,
+                     int j, long batch, const int *il, cudaStream_t s, bool global_panel, bool defer_left)
 {
     const int mp = max_m - j;
     if (global_panel) {
-        panel_global_kernel<W><<<(unsigned)batch, 256, 0, s>>>(d, dA, dipiv, dinfo, j, batch, il);
+        panel_global_kernel<W><<<(unsigned)batch, 256, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il);
     } else {
         int T = (mp + R - 1) / R;
         T = ((T + 31) / 32) * 32;
         if (T > 512) return MAGMA_ERR_NOT_SUPPORTED;
-        panel_kernel<R, W><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, j, batch, il);
+        panel_kernel<R, W><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il);
     }
     count_launch();
     MB200_CHECK_LAUNCH("panel_kernel");
 
-    // tiles: right part starts at j + jb (jb = W except on a matrix's last, narrower panel)
     // fixed size: the panel width is known here; variable size: a matrix on its last, narrower
     // panel can leave up to max_n-j-1 columns to its right
     const int max_mn = max_m < max_n ? max_m : max_n;
     const int jb_host = (max_mn - j) < W ? (max_mn - j) : W;
     const int nright_max = d.vm ? (max_n - j - 1) : (max_n - j - jb_host);
-    const int right_tiles = nright_max > 0 ? (nright_max + TN - 1) / TN : 0;
-    const int left_tiles = j > 0 ? (j + TN - 1) / TN : 0;
-    const int tiles = right_tiles + left_tiles;
-    if (tiles > 0) {
+    const int mbelow_max = d.vm ? (max_m - j - 1) : (max_m - j - jb_host);
+    // interchanges of the columns to the left: deferred to laswp_left_kernel when every step is 32
+    // wide, otherwise applied now (left tiles of swap_trsm_kernel)
+    const int left_tiles = (!defer_left && j > 0) ? (j + TN - 1) / TN : 0;
+    if (nright_max <= 0 && left_tiles == 0) return 0;
+    if (mp <= SROWS && nright_max > 0) {
+        // short panel: the whole trailing strip fits in shared memory
         static bool attr_set = false;
-        const size_t smem = sizeof(UpdSmem);
         if (!attr_set) {
-            cudaFuncSetAttribute(update_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(update_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(update_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(update_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(update_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(update_strip_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StripSmem));
             attr_set = true;
         }
-        const long grid = (long)tiles * batch;
+        const int strips = (nright_max + SW - 1) / SW;
+        const long grid = (long)strips * batch;
         if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
-        update_kernel<W><<<(unsigned)grid, UPD_THREADS, smem, s>>>(d, dA, dipiv, j, right_tiles, left_tiles,
-                                                                  batch, il);
+        update_strip_kernel<32><<<(unsigned)grid, STRIP_THREADS, sizeof(StripSmem), s>>>(d, dA, recs, j, strips, batch, il);
         count_launch();
-        MB200_CHECK_LAUNCH("update_kernel");
+        MB200_CHECK_LAUNCH("update_strip_kernel");
+        if (left_tiles > 0) {
+            swap_trsm_kernel<W><<<(unsigned)((long)left_tiles * batch), ST_THREADS, 0, s>>>(d, dA, recs, j, 0, left_tiles, batch, il);
+            count_launch();
+            MB200_CHECK_LAUNCH("swap_trsm_kernel");
+        }
+        return 0;
+    }
+    const int right_tiles = nright_max > 0 ? (nright_max + TN - 1) / TN : 0;
+    {
+        const long grid = (long)(right_tiles + left_tiles) * batch;
+        if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
+        swap_trsm_kernel<W><<<(unsigned)grid, ST_THREADS, 0, s>>>(d, dA, recs, j, right_tiles, left_tiles, batch, il);
+        count_launch();
+        MB200_CHECK_LAUNCH("swap_trsm_kernel");
+    }
+    if (mbelow_max > 0 && nright_max > 0) {
+        const int tiles_m = (mbelow_max + GM - 1) / GM, tiles_n = (nright_max + GN - 1) / GN;
+        const long grid = (long)tiles_m * tiles_n * batch;
+        if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
+        gemm_kernel<W><<<(unsigned)grid, GEMM_THREADS, 0, s>>>(d, dA, j, tiles_m, tiles_n, batch, il);
+        count_launch();
+        MB200_CHECK_LAUNCH("gemm_kernel");
     }
     return 0;
 }
 
 }  // namespace
 
+size_t lu_blocked_workspace_bytes(long batch) { return sizeof(PivRec) * (size_t)(batch > 0 ? batch : 0); }
+
 magma_int_t lu_blocked_launch(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo,
-                              long batch, const int *index_list, cudaStream_t s)
+                              long batch, const int *index_list, void *workspace, cudaStream_t s)
 {
     if (batch <= 0) return 0;
+    PivRec *recs = reinterpret_cast<PivRec *>(workspace);
     const int max_mn = max_m < max_n ? max_m : max_n;  // upper bound of min(m_b, n_b)
+    const bool defer_left = (max_m <= 512);             // every step is 32 wide
     int j = 0;
     while (j < max_mn) {
         const int mp = max_m - j;
         magma_int_t rc;
         int w;
-        if (mp <= 512)       { w = 32; rc = run_step<1, 32>(d, max_m, max_n, dA, dipiv, dinfo, j, batch, index_list, s, false); }
-        else if (mp <= 1024) { w = 16; rc = run_step<2, 16>(d, max_m, max_n, dA, dipiv, dinfo, j, batch, index_list, s, false); }
-        else if (mp <= 2048) { w = 8;  rc = run_step<4, 8>(d, max_m, max_n, dA, dipiv, dinfo, j, batch, index_list, s, false); }
-        else if (mp <= 4096) { w = 4;  rc = run_step<8, 4>(d, max_m, max_n, dA, dipiv, dinfo, j, batch, index_list, s, false); }
-        else if (mp <= 8192) { w = 2;  rc = run_step<16, 2>(d, max_m, max_n, dA, dipiv, dinfo, j, batch, index_list, s, false); }
-        else                 { w = 8;  rc = run_step<1, 8>(d, max_m, max_n, dA, dipiv, dinfo, j, batch, index_list, s, true); }
+        if (mp <= 512)       { w = 32; rc = run_step<1, 32>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left); }
+        else if (mp <= 1024) { w = 16; rc = run_step<2, 16>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left); }
+        else if (mp <= 2048) { w = 8;  rc = run_step<4, 8>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left); }
+        else if (mp <= 4096) { w = 4;  rc = run_step<8, 4>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left); }
+        else if (mp <= 8192) { w = 2;  rc = run_step<16, 2>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left); }
+        else                 { w = 8;  rc = run_step<1, 8>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, true, defer_left); }
         if (rc != 0) return rc;
         j += w;
+    }
+    if (defer_left && max_mn > 32) {
+        const int blocks = (max_mn - 1) / 32;  // column blocks that have a later panel
+        const int max_rows = max_m - 32;
+        const size_t smem = sizeof(int) * 2 * (size_t)max_rows + 16 + sizeof(double) * LSWP_COLS * (size_t)max_rows;
+        const long grid = (long)blocks * batch;
+        if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
+        laswp_left_kernel<<<(unsigned)grid, LSWP_THREADS, smem, s>>>(d, dA, dipiv, blocks, max_rows, 32, batch, index_list);
+        count_launch();
+        MB200_CHECK_LAUNCH("laswp_left_kernel");
     }
     return 0;
 }

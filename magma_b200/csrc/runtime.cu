@@ -12,23 +12,23 @@ std::atomic<int64_t> g_launches{0};
 int g_tier = 0;
 static std::atomic<int> g_init_count{0};
 
-void *queue_dscratch(magma_queue_t q, size_t bytes)
+void *queue_dscratch(magma_queue_t q, size_t bytes, int slot)
 {
-    if (q->dscratch_bytes < bytes) {
-        if (q->dscratch) {
+    if (q->dscratch_bytes[slot] < bytes) {
+        if (q->dscratch[slot]) {
             cudaStreamSynchronize(q->stream);
-            cudaFree(q->dscratch);
+            cudaFree(q->dscratch[slot]);
         }
-        q->dscratch = nullptr;
-        q->dscratch_bytes = 0;
+        q->dscratch[slot] = nullptr;
+        q->dscratch_bytes[slot] = 0;
         size_t want = bytes + bytes / 4;
-        if (cudaMalloc(&q->dscratch, want) != cudaSuccess) {
+        if (cudaMalloc(&q->dscratch[slot], want) != cudaSuccess) {
             cudaGetLastError();
             return nullptr;
         }
-        q->dscratch_bytes = want;
+        q->dscratch_bytes[slot] = want;
     }
-    return q->dscratch;
+    return q->dscratch[slot];
 }
 
 void *queue_hscratch(magma_queue_t q, size_t bytes)
@@ -212,7 +212,8 @@ void magma_queue_destroy_internal(magma_queue_t q, const char *func, const char 
         for (int i = 0; i < 2; ++i) cudaStreamDestroy(q->aux_stream[i]);
         for (int i = 0; i < 8; ++i) cudaEventDestroy(q->aux_event[i]);
     }
-    if (q->dscratch) cudaFree(q->dscratch);
+    for (int i = 0; i < 2; ++i)
+        if (q->dscratch[i]) cudaFree(q->dscratch[i]);
     if (q->hscratch) cudaFreeHost(q->hscratch);
     if (q->own_stream) cudaStreamDestroy(q->stream);
     free(q);

@@ -13,6 +13,7 @@ def flops_getrf(n):
 import os
 CONFIGS=[(32, 10000, 0), (32, 400000, 0), (16, 1000000, 1), (16, 1000000, 0), (8, 2000000, 0), (24, 400000, 0), (64, 100000, 0), (128, 50000, 0), (256, 8000, 0), (512, 4000, 0)]
 if os.environ.get('PROBE_SMALL'): CONFIGS=[c for c in CONFIGS if c[0]<=32]
+if os.environ.get('PROBE_MID'): CONFIGS=[(48,100000,0),(64,100000,0),(96,50000,0),(128,50000,0)]
 def main():
     torch.cuda.set_device(0)
     mb.magma_init()

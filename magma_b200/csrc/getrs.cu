@@ -19,184 +19,101 @@ namespace {
 constexpr int SOLVE_THREADS = 256;
 constexpr int SB = 32;  // block size along the triangle
 
-// X tile lives in smem as Bs[c*ldb_s + i], i < n, c < tr.
+// X tile lives in smem as Bs[c*ldb_s + i], i < n, c < tr (column per right-hand side: thread-per-row
+// accesses are conflict free). Xs[k*TRW + c] holds the block of unknowns just solved, rhs-contiguous,
+// so the update reads it with broadcast 128-bit loads.
+constexpr int TRW = 16;  // right-hand sides per CTA tile
 
-// L (unit or non-unit lower), no transpose: forward substitution.
-template <bool UNIT>
-__device__ void solve_lower_n(int n, int tr, const double *__restrict__ A, int ld, double *Bs, int ldb_s)
-{
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = SOLVE_THREADS / 32;
-    for (int kb = 0; kb < n; kb += SB) {
-        const int kw = (n - kb) < SB ? (n - kb) : SB;
-        // diagonal block: warp per rhs column, lane = row
-        if (wid < tr || nw < tr) {
-            double lcol[SB];
-#pragma unroll
-            for (int k = 0; k < SB; ++k)
-                lcol[k] = (k < kw && lane < kw && lane >= k) ? A[(size_t)(kb + lane) + (size_t)(kb + k) * ld] : 0.0;
-            const double dinv = (!UNIT && lane < kw) ? 1.0 / A[(size_t)(kb + lane) * (ld + 1)] : 1.0;
-            for (int c = wid; c < tr; c += nw) {
-                double x = (lane < kw) ? Bs[c * ldb_s + kb + lane] : 0.0;
-#pragma unroll
-                for (int k = 0; k < SB; ++k) {
-                    if (k < kw) {
-                        if (!UNIT && lane == k) x = x * dinv;
-                        const double xk = __shfl_sync(0xffffffffu, x, k);
-                        if (lane > k) x = fma(-lcol[k], xk, x);
-                    }
-                }
-                if (lane < kw) Bs[c * ldb_s + kb + lane] = x;
-            }
-        }
-        __syncthreads();
-        // rows below the block
-        for (int i = kb + kw + tid; i < n; i += SOLVE_THREADS) {
-            double l[SB];
-#pragma unroll
-            for (int k = 0; k < SB; ++k) l[k] = (k < kw) ? A[(size_t)i + (size_t)(kb + k) * ld] : 0.0;
-            for (int c = 0; c < tr; ++c) {
-                double s = Bs[c * ldb_s + i];
-                const double *xk = Bs + c * ldb_s + kb;
-#pragma unroll
-                for (int k = 0; k < SB; ++k)
-                    if (k < kw) s = fma(-l[k], xk[k], s);
-                Bs[c * ldb_s + i] = s;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// U (non-unit or unit upper), no transpose: backward substitution, k decreasing.
-template <bool UNIT>
-__device__ void solve_upper_n(int n, int tr, const double *__restrict__ A, int ld, double *Bs, int ldb_s)
+// One routine for the four triangular operators op(T):
+//   FWD = op(T) is lower triangular (L, or U^T): forward substitution, k increasing;
+//   else  op(T) is upper triangular (U, or L^T): backward substitution, k decreasing.
+//   TRANS: op(T)(i,k) = A[k + i*ld], else A[i + k*ld].
+// Per unknown the update order is the canonical one of oracle/lu_oracle.c.
+template <bool UNIT, bool FWD, bool TRANS>
+__device__ void solve_tri(int n, int tr, const double *__restrict__ A, int ld, double *Bs, int ldb_s, double *Xs)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = SOLVE_THREADS / 32;
     const int nblk = (n + SB - 1) / SB;
-    for (int blk = nblk - 1; blk >= 0; --blk) {
+    for (int bi = 0; bi < nblk; ++bi) {
+        const int blk = FWD ? bi : nblk - 1 - bi;
         const int kb = blk * SB;
         const int kw = (n - kb) < SB ? (n - kb) : SB;
-        if (wid < tr || nw < tr) {
-            double ucol[SB];
+        // ---- diagonal block: warp per rhs column, lane = row ---------------------------------
+        if (wid < tr) {
+            double tc[SB];  // tc[k] = op(T)(kb+lane, kb+k)
 #pragma unroll
-            for (int k = 0; k < SB; ++k)
-                ucol[k] = (k < kw && lane <= k) ? A[(size_t)(kb + lane) + (size_t)(kb + k) * ld] : 0.0;
+            for (int k = 0; k < SB; ++k) {
+                const bool need = (k < kw) && (lane < kw) && (FWD ? (lane >= k) : (lane <= k));
+                const size_t off = TRANS ? ((size_t)(kb + k) + (size_t)(kb + lane) * ld)
+                                         : ((size_t)(kb + lane) + (size_t)(kb + k) * ld);
+                tc[k] = need ? A[off] : 0.0;
+            }
             const double dinv = (!UNIT && lane < kw) ? 1.0 / A[(size_t)(kb + lane) * (ld + 1)] : 1.0;
             for (int c = wid; c < tr; c += nw) {
                 double x = (lane < kw) ? Bs[c * ldb_s + kb + lane] : 0.0;
 #pragma unroll
-                for (int k = SB - 1; k >= 0; --k) {
+                for (int kk = 0; kk < SB; ++kk) {
+                    const int k = FWD ? kk : SB - 1 - kk;
                     if (k < kw) {
                         if (!UNIT && lane == k) x = x * dinv;
                         const double xk = __shfl_sync(0xffffffffu, x, k);
-                        if (lane < k) x = fma(-ucol[k], xk, x);
+                        if (FWD ? (lane > k) : (lane < k)) x = fma(-tc[k], xk, x);
                     }
                 }
-                if (lane < kw) Bs[c * ldb_s + kb + lane] = x;
+                if (lane < kw) {
+                    Bs[c * ldb_s + kb + lane] = x;
+                    Xs[lane * TRW + c] = x;
+                }
             }
         }
         __syncthreads();
-        for (int i = tid; i < kb; i += SOLVE_THREADS) {
-            double u[SB];
+        // ---- remaining rows: thread = 2 rows x TRW rhs, k in canonical order --------------------
+        const int lo = FWD ? kb + kw : 0;
+        const int hi = FWD ? n : kb;
+        for (int i0 = lo + tid; i0 < hi; i0 += 2 * SOLVE_THREADS) {
+            const int i1 = i0 + SOLVE_THREADS;
+            const bool has1 = i1 < hi;
+            double acc0[TRW], acc1[TRW];
 #pragma unroll
-            for (int k = 0; k < SB; ++k) u[k] = (k < kw) ? A[(size_t)i + (size_t)(kb + k) * ld] : 0.0;
-            for (int c = 0; c < tr; ++c) {
-                double s = Bs[c * ldb_s + i];
-                const double *xk = Bs + c * ldb_s + kb;
-#pragma unroll
-                for (int k = SB - 1; k >= 0; --k)
-                    if (k < kw) s = fma(-u[k], xk[k], s);
-                Bs[c * ldb_s + i] = s;
+            for (int c = 0; c < TRW; ++c) {
+                acc0[c] = (c < tr) ? Bs[c * ldb_s + i0] : 0.0;
+                acc1[c] = (c < tr && has1) ? Bs[c * ldb_s + i1] : 0.0;
             }
-        }
-        __syncthreads();
-    }
-}
-
-// U^T (lower-triangular operator): forward. Element (i,k) of U^T is A[k + i*ld].
-template <bool UNIT>
-__device__ void solve_upper_t(int n, int tr, const double *__restrict__ A, int ld, double *Bs, int ldb_s)
-{
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = SOLVE_THREADS / 32;
-    for (int kb = 0; kb < n; kb += SB) {
-        const int kw = (n - kb) < SB ? (n - kb) : SB;
-        if (wid < tr || nw < tr) {
-            double tcol[SB];  // tcol[k] = U^T(kb+lane, kb+k) = A[(kb+k) + (kb+lane)*ld], lane >= k
 #pragma unroll
-            for (int k = 0; k < SB; ++k)
-                tcol[k] = (k < kw && lane < kw && lane >= k) ? A[(size_t)(kb + k) + (size_t)(kb + lane) * ld] : 0.0;
-            const double dinv = (!UNIT && lane < kw) ? 1.0 / A[(size_t)(kb + lane) * (ld + 1)] : 1.0;
-            for (int c = wid; c < tr; c += nw) {
-                double x = (lane < kw) ? Bs[c * ldb_s + kb + lane] : 0.0;
+            for (int k8 = 0; k8 < SB; k8 += 8) {
+                const int kbase = FWD ? k8 : SB - 8 - k8;
+                double t0[8], t1[8];
 #pragma unroll
-                for (int k = 0; k < SB; ++k) {
+                for (int u = 0; u < 8; ++u) {
+                    const int k = kbase + u;
+                    const bool ok = k < kw;
+                    const size_t o0 = TRANS ? ((size_t)(kb + k) + (size_t)i0 * ld) : ((size_t)i0 + (size_t)(kb + k) * ld);
+                    const size_t o1 = TRANS ? ((size_t)(kb + k) + (size_t)i1 * ld) : ((size_t)i1 + (size_t)(kb + k) * ld);
+                    t0[u] = ok ? A[o0] : 0.0;
+                    t1[u] = (ok && has1) ? A[o1] : 0.0;
+                }
+#pragma unroll
+                for (int uu = 0; uu < 8; ++uu) {
+                    const int u = FWD ? uu : 7 - uu;
+                    const int k = kbase + u;
                     if (k < kw) {
-                        if (!UNIT && lane == k) x = x * dinv;
-                        const double xk = __shfl_sync(0xffffffffu, x, k);
-                        if (lane > k) x = fma(-tcol[k], xk, x);
+#pragma unroll
+                        for (int c = 0; c < TRW; c += 2) {
+                            const double2 x = *reinterpret_cast<const double2 *>(&Xs[k * TRW + c]);
+                            acc0[c] = fma(-t0[u], x.x, acc0[c]);
+                            acc0[c + 1] = fma(-t0[u], x.y, acc0[c + 1]);
+                            acc1[c] = fma(-t1[u], x.x, acc1[c]);
+                            acc1[c + 1] = fma(-t1[u], x.y, acc1[c + 1]);
+                        }
                     }
                 }
-                if (lane < kw) Bs[c * ldb_s + kb + lane] = x;
             }
-        }
-        __syncthreads();
-        for (int i = kb + kw + tid; i < n; i += SOLVE_THREADS) {
-            double t[SB];
 #pragma unroll
-            for (int k = 0; k < SB; ++k) t[k] = (k < kw) ? A[(size_t)(kb + k) + (size_t)i * ld] : 0.0;
-            for (int c = 0; c < tr; ++c) {
-                double s = Bs[c * ldb_s + i];
-                const double *xk = Bs + c * ldb_s + kb;
-#pragma unroll
-                for (int k = 0; k < SB; ++k)
-                    if (k < kw) s = fma(-t[k], xk[k], s);
-                Bs[c * ldb_s + i] = s;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// L^T (upper-triangular operator): backward. Element (i,k) of L^T is A[k + i*ld], k > i.
-template <bool UNIT>
-__device__ void solve_lower_t(int n, int tr, const double *__restrict__ A, int ld, double *Bs, int ldb_s)
-{
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = SOLVE_THREADS / 32;
-    const int nblk = (n + SB - 1) / SB;
-    for (int blk = nblk - 1; blk >= 0; --blk) {
-        const int kb = blk * SB;
-        const int kw = (n - kb) < SB ? (n - kb) : SB;
-        if (wid < tr || nw < tr) {
-            double tcol[SB];
-#pragma unroll
-            for (int k = 0; k < SB; ++k)
-                tcol[k] = (k < kw && lane <= k) ? A[(size_t)(kb + k) + (size_t)(kb + lane) * ld] : 0.0;
-            const double dinv = (!UNIT && lane < kw) ? 1.0 / A[(size_t)(kb + lane) * (ld + 1)] : 1.0;
-            for (int c = wid; c < tr; c += nw) {
-                double x = (lane < kw) ? Bs[c * ldb_s + kb + lane] : 0.0;
-#pragma unroll
-                for (int k = SB - 1; k >= 0; --k) {
-                    if (k < kw) {
-                        if (!UNIT && lane == k) x = x * dinv;
-                        const double xk = __shfl_sync(0xffffffffu, x, k);
-                        if (lane < k) x = fma(-tcol[k], xk, x);
-                    }
+            for (int c = 0; c < TRW; ++c) {
+                if (c < tr) {
+                    Bs[c * ldb_s + i0] = acc0[c];
+                    if (has1) Bs[c * ldb_s + i1] = acc1[c];
                 }
-                if (lane < kw) Bs[c * ldb_s + kb + lane] = x;
-            }
-        }
-        __syncthreads();
-        for (int i = tid; i < kb; i += SOLVE_THREADS) {
-            double t[SB];
-#pragma unroll
-            for (int k = 0; k < SB; ++k) t[k] = (k < kw) ? A[(size_t)(kb + k) + (size_t)i * ld] : 0.0;
-            for (int c = 0; c < tr; ++c) {
-                double s = Bs[c * ldb_s + i];
-                const double *xk = Bs + c * ldb_s + kb;
-#pragma unroll
-                for (int k = SB - 1; k >= 0; --k)
-                    if (k < kw) s = fma(-t[k], xk[k], s);
-                Bs[c * ldb_s + i] = s;
             }
         }
         __syncthreads();
@@ -225,7 +142,7 @@ __device__ void build_perm(int n, const int *__restrict__ ipiv, int *perm, int *
 }
 
 // mode: 0 getrs NoTrans, 1 getrs Trans, 2 laswp only (k1..k2), 3.. trsm variants
-__global__ void __launch_bounds__(SOLVE_THREADS)
+__global__ void __launch_bounds__(SOLVE_THREADS, 2)
 getrs_kernel(int trans, int n, int nrhs, int tr_max, double **__restrict__ dA, int ldda, int **__restrict__ dipiv,
              double **__restrict__ dB, int lddb, int rhs_tiles)
 {
@@ -236,8 +153,10 @@ getrs_kernel(int trans, int n, int nrhs, int tr_max, double **__restrict__ dA, i
     const int tr = (nrhs - c0) < tr_max ? (nrhs - c0) : tr_max;
     const int ldb_s = n | 1;  // odd stride: the per-column diagonal-block accesses spread over banks
     double *Bs = reinterpret_cast<double *>(smem_raw);
-    int *perm = reinterpret_cast<int *>(Bs + (size_t)tr_max * ldb_s);
+    double *Xs = Bs + (((size_t)tr_max * ldb_s + 1) & ~(size_t)1);  // 16-byte aligned
+    int *perm = reinterpret_cast<int *>(Xs + SB * TRW);
     int *sipiv = perm + n;
+    for (int i = threadIdx.x; i < SB * TRW; i += SOLVE_THREADS) Xs[i] = 0.0;
     const double *__restrict__ A = dA[b];
     double *__restrict__ B = dB[b] + (size_t)c0 * lddb;
 
@@ -248,8 +167,8 @@ getrs_kernel(int trans, int n, int nrhs, int tr_max, double **__restrict__ dA, i
             Bs[c * ldb_s + i] = B[perm[i] + (size_t)c * lddb];
         }
         __syncthreads();
-        solve_lower_n<true>(n, tr, A, ldda, Bs, ldb_s);
-        solve_upper_n<false>(n, tr, A, ldda, Bs, ldb_s);
+        solve_tri<true, true, false>(n, tr, A, ldda, Bs, ldb_s, Xs);    // L y = P b (unit)
+        solve_tri<false, false, false>(n, tr, A, ldda, Bs, ldb_s, Xs);  // U x = y
         for (int idx = threadIdx.x; idx < n * tr; idx += SOLVE_THREADS) {
             const int i = idx % n, c = idx / n;
             B[i + (size_t)c * lddb] = Bs[c * ldb_s + i];
@@ -260,8 +179,8 @@ getrs_kernel(int trans, int n, int nrhs, int tr_max, double **__restrict__ dA, i
             Bs[c * ldb_s + i] = B[i + (size_t)c * lddb];
         }
         __syncthreads();
-        solve_upper_t<false>(n, tr, A, ldda, Bs, ldb_s);
-        solve_lower_t<true>(n, tr, A, ldda, Bs, ldb_s);
+        solve_tri<false, true, true>(n, tr, A, ldda, Bs, ldb_s, Xs);   // U^T y = b
+        solve_tri<true, false, true>(n, tr, A, ldda, Bs, ldb_s, Xs);   // L^T x = y (unit)
         // inverse of the forward interchanges: x[perm[i]] = y[i]
         for (int idx = threadIdx.x; idx < n * tr; idx += SOLVE_THREADS) {
             const int i = idx % n, c = idx / n;
@@ -271,7 +190,7 @@ getrs_kernel(int trans, int n, int nrhs, int tr_max, double **__restrict__ dA, i
 }
 
 // standalone trsm, side = Left.  B <- alpha * op(A)^-1 B
-__global__ void __launch_bounds__(SOLVE_THREADS)
+__global__ void __launch_bounds__(SOLVE_THREADS, 2)
 trsm_left_kernel(int uplo, int trans, int diag, int n, int nrhs, int tr_max, double alpha,
                  double **__restrict__ dA, int ldda, double **__restrict__ dB, int lddb, int rhs_tiles)
 {
@@ -282,8 +201,10 @@ trsm_left_kernel(int uplo, int trans, int diag, int n, int nrhs, int tr_max, dou
     const int tr = (nrhs - c0) < tr_max ? (nrhs - c0) : tr_max;
     const int ldb_s = n | 1;
     double *Bs = reinterpret_cast<double *>(smem_raw);
+    double *Xs = Bs + (((size_t)tr_max * ldb_s + 1) & ~(size_t)1);  // 16-byte aligned
     const double *__restrict__ A = dA[b];
     double *__restrict__ B = dB[b] + (size_t)c0 * lddb;
+    for (int i = threadIdx.x; i < SB * TRW; i += SOLVE_THREADS) Xs[i] = 0.0;
     for (int idx = threadIdx.x; idx < n * tr; idx += SOLVE_THREADS) {
         const int i = idx % n, c = idx / n;
         Bs[c * ldb_s + i] = alpha * B[i + (size_t)c * lddb];
@@ -292,10 +213,10 @@ trsm_left_kernel(int uplo, int trans, int diag, int n, int nrhs, int tr_max, dou
     const bool unit = (diag == MagmaUnit);
     const bool lower = (uplo == MagmaLower);
     const bool nt = (trans == MagmaNoTrans);
-    if (lower && nt) { if (unit) solve_lower_n<true>(n, tr, A, ldda, Bs, ldb_s); else solve_lower_n<false>(n, tr, A, ldda, Bs, ldb_s); }
-    else if (!lower && nt) { if (unit) solve_upper_n<true>(n, tr, A, ldda, Bs, ldb_s); else solve_upper_n<false>(n, tr, A, ldda, Bs, ldb_s); }
-    else if (!lower && !nt) { if (unit) solve_upper_t<true>(n, tr, A, ldda, Bs, ldb_s); else solve_upper_t<false>(n, tr, A, ldda, Bs, ldb_s); }
-    else { if (unit) solve_lower_t<true>(n, tr, A, ldda, Bs, ldb_s); else solve_lower_t<false>(n, tr, A, ldda, Bs, ldb_s); }
+    if (lower && nt) { if (unit) solve_tri<true, true, false>(n, tr, A, ldda, Bs, ldb_s, Xs); else solve_tri<false, true, false>(n, tr, A, ldda, Bs, ldb_s, Xs); }
+    else if (!lower && nt) { if (unit) solve_tri<true, false, false>(n, tr, A, ldda, Bs, ldb_s, Xs); else solve_tri<false, false, false>(n, tr, A, ldda, Bs, ldb_s, Xs); }
+    else if (!lower && !nt) { if (unit) solve_tri<true, true, true>(n, tr, A, ldda, Bs, ldb_s, Xs); else solve_tri<false, true, true>(n, tr, A, ldda, Bs, ldb_s, Xs); }
+    else { if (unit) solve_tri<true, false, true>(n, tr, A, ldda, Bs, ldb_s, Xs); else solve_tri<false, false, true>(n, tr, A, ldda, Bs, ldb_s, Xs); }
     for (int idx = threadIdx.x; idx < n * tr; idx += SOLVE_THREADS) {
         const int i = idx % n, c = idx / n;
         B[i + (size_t)c * lddb] = Bs[c * ldb_s + i];
@@ -374,8 +295,9 @@ int pick_tr(int n, int nrhs, size_t &smem)
     const size_t cap = 200 * 1024;
     const int ldb_s = n | 1;
     int tr = nrhs < 16 ? nrhs : 16;
-    while (tr > 1 && (size_t)tr * ldb_s * 8 + (size_t)n * 8 > cap) tr >>= 1;
-    smem = (size_t)tr * ldb_s * 8 + (size_t)n * 8;
+    const size_t fixed = (size_t)SB * TRW * 8 + (size_t)n * 8 + 8;  // Xs + perm/ipiv + alignment pad
+    while (tr > 1 && (size_t)tr * ldb_s * 8 + fixed > cap) tr >>= 1;
+    smem = (size_t)tr * ldb_s * 8 + fixed;
     return smem <= 227 * 1024 ? tr : 0;
 }
 

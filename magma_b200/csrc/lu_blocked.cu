@@ -469,18 +469,37 @@ gemm_kernel(Dims d, double **__restrict__ dA, int j, int tiles_m, int tiles_n, l
                 acc[2 * h + 1][2 * q + cc] = v1;
             }
         }
+    // operands: asynchronous copies, all in flight together with the C loads above
     const double *__restrict__ L21 = A + (size_t)j * ld;  // column j, absolute rows
     const double *__restrict__ U12 = A + (size_t)j;       // row j, absolute columns
-#pragma unroll 4
-    for (int idx = tid; idx < W * GM; idx += GEMM_THREADS) {
-        const int r = idx & (GM - 1), k = idx / GM;
-        As[idx] = (r < rows && k < jb) ? L21[(size_t)(r0 + r) + (size_t)k * ld] : 0.0;
+    if (vec_ok && (r0 & 1) == 0) {
+#pragma unroll
+        for (int idx = tid; idx < W * GM / 2; idx += GEMM_THREADS) {
+            const int r = (idx & (GM / 2 - 1)) * 2, k = idx / (GM / 2);
+            const double *src = &L21[(size_t)(r0 + r) + (size_t)k * ld];
+            if (r + 1 < rows && k < jb) {
+                cp_async16(&As[k * GM + r], src, true);
+            } else {  // ragged tail: last valid row alone, everything else zero-filled
+                const bool ok1 = (r < rows) && (k < jb);
+                cp_async8(&As[k * GM + r], ok1 ? src : A, ok1);
+                cp_async8(&As[k * GM + r + 1], A, false);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int idx = tid; idx < W * GM; idx += GEMM_THREADS) {
+            const int r = idx & (GM - 1), k = idx / GM;
+            const bool ok = (r < rows) && (k < jb);
+            cp_async8(&As[idx], ok ? &L21[(size_t)(r0 + r) + (size_t)k * ld] : A, ok);
+        }
     }
-#pragma unroll 4
+#pragma unroll
     for (int idx = tid; idx < W * GN; idx += GEMM_THREADS) {
         const int k = idx % W, c = idx / W;  // k fast: contiguous in global memory
-        Bs[k * GN + c] = (c < cols && k < jb) ? U12[(size_t)k + (size_t)(c0 + c) * ld] : 0.0;
+        const bool ok = (c < cols) && (k < jb);
+        cp_async8(&Bs[k * GN + c], ok ? &U12[(size_t)k + (size_t)(c0 + c) * ld] : A, ok);
     }
+    cp_async_wait_all();
     __syncthreads();
 
 #pragma unroll 4

@@ -408,6 +408,10 @@ magma_int_t lu_small_launch(const Dims &d, int max_m, int max_n, double **dA, in
                             cudaStream_t s)
 {
     if (max_m > 32 || max_n > 32 || batch <= 0) return -100;
+    if (!d.vm && d.m == d.n && index_list == nullptr && g_small_rows != 9) {  // 9: force the generic kernel (tests)
+        const magma_int_t rc = lu_sq_launch(d.n, dA, d.ldda, dipiv, dinfo, nrhs, dB, lddb, batch, s);
+        if (rc != -100) return rc;
+    }
     if (nrhs == 0) return dispatch_n<0>(max_m, max_n, d, dA, dipiv, dinfo, dB, lddb, batch, index_list, s);
     if (nrhs == 1) return dispatch_n<1>(max_m, max_n, d, dA, dipiv, dinfo, dB, lddb, batch, index_list, s);
     return -100;

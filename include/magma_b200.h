@@ -302,6 +302,8 @@ double magma_b200_hbm_copy_gbs(size_t bytes, magma_queue_t queue);
 int64_t magma_b200_launch_count(void);
 /* Force a tier for tests/benches: 0 = auto, 1 = register/warp (small), 2 = blocked. */
 void magma_b200_set_tier(int tier);
+/* Largest max(m,n) routed to the register-file tier (lu_mid.cu), 32..128; for tuning sweeps. */
+void magma_b200_set_mid_max(int n);
 /* Register tier layout override for tuning sweeps: rows per lane (1 or 2), 0 = tuned default. */
 void magma_b200_set_small_rows(int rows);
 

@@ -88,6 +88,7 @@ SIGNATURES = {
     "magma_b200_launch_count": (i64, []),
     "magma_b200_set_tier": (None, [i32]),
     "magma_b200_set_small_rows": (None, [i32]),
+    "magma_b200_set_mid_max": (None, [i32]),
     "magmaf_dgetrf_batched_": (None, [vp] * 9),
     "magmaf_dgetrs_batched_": (None, [cstr] + [vp] * 10),
     "magmaf_dgesv_batched_": (None, [vp] * 11),

@@ -28,6 +28,10 @@ Dims uniform_dims(int m, int n, int ldda)
 // Grid-x limits: batches above 2^31-1 CTAs are split here, never inside a kernel.
 constexpr long MAX_CHUNK = 1L << 24;
 
+// Largest dimension routed to the register-file tier (lu_mid.cu); above it the blocked tier runs.
+// Measured crossover on B200 (tools/gpu_probe.py, PROBE_MID): see DESIGN.md "tiers and crossovers".
+int g_mid_max = 128;
+
 }  // namespace
 
 extern "C" {
@@ -95,6 +99,8 @@ magma_int_t magma_dgetrf_batched(magma_int_t m, magma_int_t n, double **dA_array
         if (m <= 32 && n <= 32 && g_tier != 2)
             rc = lu_small_launch(d, m, n, dA_array + off, ipiv_array + off, info_array + off, 0, nullptr, 0, cnt,
                                  nullptr, s);
+        else if (m <= g_mid_max && n <= g_mid_max && g_tier != 2)
+            rc = lu_mid_launch(d, m, n, dA_array + off, ipiv_array + off, info_array + off, cnt, nullptr, s);
         if (rc == -100) {
             void *ws = queue_dscratch(queue, lu_blocked_workspace_bytes(cnt));
             if (!ws) {
@@ -409,6 +415,8 @@ void magma_idisplace_pointers(magma_int_t **output_array, magma_int_t **input_ar
 // ---------------------------------------------------------------------------------------------
 // Additions
 // ---------------------------------------------------------------------------------------------
+void magma_b200_set_mid_max(int n) { g_mid_max = n < 32 ? 32 : (n > 128 ? 128 : n); }
+
 void magma_b200_dlarnv_uniform(magma_int_t *iseed, int64_t n, double *dx, magma_queue_t queue)
 {
     const unsigned long long A = 33952834046453ull, MASK = (1ull << 48) - 1ull;

@@ -89,6 +89,10 @@ magma_int_t lu_small_launch(const Dims &d, int max_m, int max_n, double **dA, in
 magma_int_t lu_sq_launch(int n, double **dA, int ldda, int **dipiv, int *dinfo, int nrhs, double **dB,
                          int lddb, long batch, cudaStream_t s);
 
+// lu_mid.cu: whole matrix in the register file of one CTA, 32 < max(m,n) <= 128; -100 = not covered
+magma_int_t lu_mid_launch(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo,
+                          long batch, const int *index_list, cudaStream_t s);
+
 // lu_blocked.cu: blocked right-looking LU for any m x n (two kernels per panel step).
 // `workspace` must hold lu_blocked_workspace_bytes(batch) bytes (one 512-byte pivot record per matrix).
 size_t lu_blocked_workspace_bytes(long batch);

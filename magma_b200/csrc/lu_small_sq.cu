@@ -329,8 +329,12 @@ struct SqsSmem {           // one per matrix in flight (fused-solve variant only
     double dinv[N];        // 1 / u(i,i)
 };
 
-template <int N, int G, int NRHS, bool LDN, int MINB>
-__global__ void __launch_bounds__(WPC * 32, MINB)
+// WC warps per CTA; LOCK: one CTA-wide barrier per column step keeps the warps of a CTA on the same
+// instructions. The unrolled body is ~50 KB of SASS, more than the SM's instruction cache: with the
+// warps drifting apart ncu showed the GPC instruction cache at 87% of its request peak and the
+// issue rate capped near 45%; in lockstep every fetched line serves all warps of the CTA.
+template <int N, int G, int NRHS, bool LDN, int MINB, int WC, bool LOCK>
+__global__ void __launch_bounds__(WC * 32, MINB)
 lu_sqs_kernel(double *const *__restrict__ dA, int *const *__restrict__ dipiv, int *__restrict__ dinfo,
               double *const *__restrict__ dB, int ldda, long batch)
 {
@@ -344,12 +348,16 @@ lu_sqs_kernel(double *const *__restrict__ dA, int *const *__restrict__ dipiv, in
     const int sub = lane % G;
     const unsigned gmask = ((1u << G) - 1u) << (grp * G);
 
-    const long slot = ((long)blockIdx.x * WPC + wid) * GPW + grp;
+    // (A persistent-warp variant that fetched the next matrices' pointers and pulled their lines into
+    // L2 one pass ahead removed the load prologue from the stall profile but was not faster: the
+    // kernel is bound by the LSU/shuffle pipe, not by load latency. profiles/README.md, round 1.)
+    const size_t ld = LDN ? (size_t)N : (size_t)ldda;
+    const long slot = ((long)blockIdx.x * WC + wid) * GPW + grp;
     const bool valid = slot < batch;
     const long b = valid ? slot : batch - 1;  // spare groups redo the last matrix, stores suppressed
-
     double *__restrict__ A = dA[b];
-    const size_t ld = LDN ? (size_t)N : (size_t)ldda;
+    double *Bcur = NRHS ? dB[b] : nullptr;
+    int *const ip = dipiv[b];  // fetched up front: the pivot store at the end must not wait on a pointer load
 
     double a[R][N];
     double rb[R];
@@ -367,7 +375,7 @@ lu_sqs_kernel(double *const *__restrict__ dA, int *const *__restrict__ dipiv, in
     }
     double *B = nullptr;
     if (NRHS) {
-        B = dB[b];
+        B = Bcur;
 #pragma unroll
         for (int r = 0; r < R; ++r) rb[r] = ldg64(B + sub + r * G);
     }
@@ -375,6 +383,7 @@ lu_sqs_kernel(double *const *__restrict__ dA, int *const *__restrict__ dipiv, in
 
 #pragma unroll
     for (int i = 0; i < N; ++i) {
+        if (LOCK) __syncthreads();
         // ---- pivot search: high words first ------------------------------------------------------
         bool act[R];
         unsigned h[R];
@@ -446,7 +455,6 @@ lu_sqs_kernel(double *const *__restrict__ dA, int *const *__restrict__ dipiv, in
 #pragma unroll
                 for (int j = 0; j < N; ++j) A[pos[r] + (size_t)j * ld] = a[r][j];
             }
-            int *ip = dipiv[b];
 #pragma unroll
             for (int r = 0; r < R; ++r) ip[sub + r * G] = myipiv[r];
             if (sub == 0) dinfo[b] = zmask ? __ffs((int)zmask) : 0;
@@ -483,7 +491,6 @@ lu_sqs_kernel(double *const *__restrict__ dA, int *const *__restrict__ dipiv, in
                     A[row + (size_t)col * ld] = sm.stage[e];
                 }
             }
-            int *ip = dipiv[b];
 #pragma unroll
             for (int r = 0; r < R; ++r) ip[sub + r * G] = myipiv[r];
             if (sub == 0) dinfo[b] = zmask ? __ffs((int)zmask) : 0;
@@ -515,23 +522,23 @@ lu_sqs_kernel(double *const *__restrict__ dA, int *const *__restrict__ dipiv, in
     }
 }
 
-template <int N, int G, int NRHS, int MINB>
+template <int N, int G, int NRHS, int MINB, int WC, bool LOCK>
 magma_int_t launch_sqs(double **dA, int ldda, int **dipiv, int *dinfo, double **dB, long batch, cudaStream_t s)
 {
     constexpr int GPW = 32 / G;
-    const long per_cta = WPC * GPW;
+    const long per_cta = WC * GPW;
     const long grid = (batch + per_cta - 1) / per_cta;
     const size_t smem = NRHS ? sizeof(SqsSmem<N>) * per_cta : 0;
     static bool once = false;
     if (!once) {
-        cudaFuncSetAttribute(lu_sqs_kernel<N, G, NRHS, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(lu_sqs_kernel<N, G, NRHS, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(lu_sqs_kernel<N, G, NRHS, true, MINB, WC, LOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(lu_sqs_kernel<N, G, NRHS, false, MINB, WC, LOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         once = true;
     }
     if (ldda == N)
-        lu_sqs_kernel<N, G, NRHS, true, MINB><<<(unsigned)grid, WPC * 32, smem, s>>>(dA, dipiv, dinfo, dB, ldda, batch);
+        lu_sqs_kernel<N, G, NRHS, true, MINB, WC, LOCK><<<(unsigned)grid, WC * 32, smem, s>>>(dA, dipiv, dinfo, dB, ldda, batch);
     else
-        lu_sqs_kernel<N, G, NRHS, false, MINB><<<(unsigned)grid, WPC * 32, smem, s>>>(dA, dipiv, dinfo, dB, ldda, batch);
+        lu_sqs_kernel<N, G, NRHS, false, MINB, WC, LOCK><<<(unsigned)grid, WC * 32, smem, s>>>(dA, dipiv, dinfo, dB, ldda, batch);
     count_launch();
     MB200_CHECK_LAUNCH("lu_sqs_kernel");
     return 0;
@@ -570,16 +577,20 @@ magma_int_t lu_sq_launch(int n, double **dA, int ldda, int **dipiv, int *dinfo, 
     if (batch <= 0 || nrhs > 1) return -100;
     if (nrhs == 0) {
         switch (n) {
-            case 8: return launch_sqs<8, 4, 0, 8>(dA, ldda, dipiv, dinfo, dB, batch, s);
-            case 16: return launch_sqs<16, 8, 0, 4>(dA, ldda, dipiv, dinfo, dB, batch, s);
-            case 32: return launch_sq<32, 32, 1, 0, 4>(dA, ldda, dipiv, dinfo, dB, batch, s);
+            case 8: return launch_sqs<8, 4, 0, 8, 4, false>(dA, ldda, dipiv, dinfo, dB, batch, s);
+            case 16:
+                if (g_small_rows == 4) return launch_sqs<16, 8, 0, 4, 4, false>(dA, ldda, dipiv, dinfo, dB, batch, s);
+                return launch_sqs<16, 8, 0, 5, 4, false>(dA, ldda, dipiv, dinfo, dB, batch, s);
+            case 32: return g_small_rows == 3 ? launch_sq<32, 32, 1, 0, 4>(dA, ldda, dipiv, dinfo, dB, batch, s) : -100;
             default: return -100;
         }
     }
     switch (n) {
-        case 8: return launch_sqs<8, 4, 1, 8>(dA, ldda, dipiv, dinfo, dB, batch, s);
-        case 16: return launch_sqs<16, 8, 1, 4>(dA, ldda, dipiv, dinfo, dB, batch, s);
-        case 32: return launch_sq<32, 32, 1, 1, 4>(dA, ldda, dipiv, dinfo, dB, batch, s);
+        case 8: return launch_sqs<8, 4, 1, 8, 4, false>(dA, ldda, dipiv, dinfo, dB, batch, s);
+        case 16:
+            if (g_small_rows == 4) return launch_sqs<16, 8, 1, 4, 4, false>(dA, ldda, dipiv, dinfo, dB, batch, s);
+            return launch_sqs<16, 8, 1, 5, 4, false>(dA, ldda, dipiv, dinfo, dB, batch, s);
+        case 32: return g_small_rows == 3 ? launch_sq<32, 32, 1, 1, 4>(dA, ldda, dipiv, dinfo, dB, batch, s) : -100;
         default: return -100;
     }
 }

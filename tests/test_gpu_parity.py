@@ -130,6 +130,43 @@ def test_getrf_blocked_ldda(gpu_queue, n, ldda):
     check_against_oracle(gpu_queue, A0, n, ldda=ldda)
 
 
+# ---- register-file tier (lu_mid.cu), forced up to its full range ------------------------------------
+
+@pytest.fixture
+def mid_tier_128():
+    mb.set_mid_max(128)
+    yield
+    mb.set_mid_max(128)
+
+
+@pytest.mark.parametrize("m,n,batch", [(33, 33, 21), (64, 64, 9), (65, 65, 9), (96, 96, 7), (100, 100, 5), (128, 128, 6),
+                                       (128, 40, 5), (40, 128, 5), (97, 90, 4), (33, 128, 3), (128, 33, 3), (127, 121, 3),
+                                       (1, 100, 3), (100, 1, 3)])
+def test_getrf_mid_tier(gpu_queue, mid_tier_128, m, n, batch):
+    A0, _ = oracle.random_batch(batch, m, n)
+    check_against_oracle(gpu_queue, A0, m)
+
+
+@pytest.mark.parametrize("n,ldda", [(100, 128), (100, 101), (65, 67), (128, 130)])
+def test_getrf_mid_tier_ldda(gpu_queue, mid_tier_128, n, ldda):
+    A0, _ = oracle.random_batch(6, n, n)
+    check_against_oracle(gpu_queue, A0, n, ldda=ldda)
+
+
+def test_mid_tier_singular_and_ties(gpu_queue, mid_tier_128):
+    rng = np.random.default_rng(5)
+    for n in (40, 72, 128):
+        mats = [np.zeros((n, n)), np.ones((n, n)), np.eye(n), np.fliplr(np.eye(n)),
+                rng.integers(-3, 4, size=(n, n)).astype(float)]
+        Z = rng.random((n, n))
+        Z[:, n // 3] = 0.0          # an exactly zero column of the stored layout
+        mats.append(Z)
+        Z2 = rng.random((n, n))
+        Z2[n // 2:, :] = Z2[:n - n // 2, :]   # rank deficient: zero pivots late in the factorisation
+        mats.append(Z2)
+        check_against_oracle(gpu_queue, np.stack(mats), n)
+
+
 def test_blocked_tier_on_small_sizes(gpu_queue):
     """Force the blocked kernels onto sizes the register tier normally takes."""
     mb.set_tier(2)

@@ -29,6 +29,7 @@ if ROOT not in sys.path:
 METRIC = "batched dgetrf/dgesv GFLOP/s (FLOPS_DGETRF + FLOPS_DGETRS, testing/flops.h)"
 UNIT = "GFLOP/s"
 N_HEAD, NRHS_HEAD, BATCH_HEAD = 16, 1, 1_000_000
+KERNEL_HEAD = "lu_sqs_kernel<16,8,1>"  # the one kernel a headline step launches (magma_b200/csrc/lu_small_sq.cu)
 
 
 def flops_getrf(m, n):
@@ -267,12 +268,12 @@ def main():
     value = fl_mat * batch * world * K / (total_ms * 1e-3) / 1e9
     achieved = by_mat * batch / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": "lu_small_kernel<16,16,1>", "peak_source": peak_src,
+                "traffic": None, "kernel": KERNEL_HEAD, "peak_source": peak_src,
                 "alg_bytes_per_launch": by_mat * batch, "launch_ms": kern_ms}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get("lu_small_kernel<16,16,1>")
+            roofline["traffic"] = json.load(open(tr)).get(KERNEL_HEAD)
         except Exception:
             pass
     del bufs

@@ -216,14 +216,17 @@ magma_int_t magma_dgesv_batched(magma_int_t n, magma_int_t nrhs, double **dA_arr
 }
 
 // ---------------------------------------------------------------------------------------------
-// Variable-size LU. Workspace layout (ints): [ idx_small (batch) | idx_big (batch) | counts (8) ].
+// Variable-size LU. Workspace layout (ints): [ 5 index lists of `batch` | counts (8) ], then the blocked
+// tier's pivot records. Matrices are binned by max(m, n) and every bin runs the tier built for it.
 // ---------------------------------------------------------------------------------------------
-static size_t vbatched_lists_bytes(long batch) { return (((size_t)(2 * batch + 8) * sizeof(int)) + 511) & ~(size_t)511; }
+static size_t vbatched_lists_bytes(long batch) { return (((size_t)(5 * batch + 8) * sizeof(int)) + 511) & ~(size_t)511; }
 static size_t vbatched_work_bytes(long batch) { return vbatched_lists_bytes(batch) + lu_blocked_workspace_bytes(batch); }
 
+// known[c] >= 0: size of bin c (read back by the synchronous driver); < 0: unknown (asynchronous expert
+// entries: every list is pre-filled with -1 and launched over `batch` slots, CTAs that draw -1 exit).
 static magma_int_t vbatched_run(magma_int_t *m, magma_int_t *n, int max_m, int max_n, double **dA_array,
                                 magma_int_t *ldda, magma_int_t **ipiv_array, magma_int_t *info_array, void *work,
-                                long batch, magma_queue_t queue, int known_small, int known_big)
+                                long batch, magma_queue_t queue, const int *known)
 {
     cudaStream_t s = queue->stream;
     Dims d;
@@ -238,26 +241,26 @@ static magma_int_t vbatched_run(magma_int_t *m, magma_int_t *n, int max_m, int m
     if (max_m <= 32 && max_n <= 32 && g_tier != 2)
         return lu_small_launch(d, max_m, max_n, dA_array, ipiv_array, info_array, 0, nullptr, 0, batch, nullptr, s);
 
-    int *idx_small = (int *)work;
-    int *idx_big = idx_small + batch;
-    int *counts = idx_big + batch;
+    int *lists = (int *)work;
+    int *counts = lists + 5 * batch;
     void *recs = (char *)work + vbatched_lists_bytes(batch);
-    long ns = known_small, nbig = known_big;
-    if (ns < 0) {
-        // expert (asynchronous) entry: the bin sizes are unknown on the host and reading them back
-        // would block, so both lists are pre-filled with -1 and each tier is launched over `batch`
-        // slots; CTAs that draw a -1 exit at once.
-        cudaMemsetAsync(idx_small, 0xFF, sizeof(int) * 2 * (size_t)batch, s);
-        ns = nbig = batch;
-    }
-    vbatched_partition_launch(m, n, batch, idx_small, idx_big, counts, s);
+    long cnt[5];
+    for (int c = 0; c < 5; ++c) cnt[c] = known ? known[c] : batch;
+    if (!known) cudaMemsetAsync(lists, 0xFF, sizeof(int) * 5 * (size_t)batch, s);
+    const int mid_max = (g_tier == 2) ? 32 : g_mid_max;
+    vbatched_partition_launch(m, n, batch, lists, counts, mid_max, s);
     magma_int_t rc = 0;
-    if (ns > 0 && g_tier != 2)
-        rc = lu_small_launch(d, 32, 32, dA_array, ipiv_array, info_array, 0, nullptr, 0, ns, idx_small, s);
-    else if (ns > 0)
-        rc = lu_blocked_launch(d, 32, 32, dA_array, ipiv_array, info_array, ns, idx_small, recs, s);
-    if (rc != 0) return rc;
-    if (nbig > 0) rc = lu_blocked_launch(d, max_m, max_n, dA_array, ipiv_array, info_array, nbig, idx_big, recs, s);
+    if (cnt[0] > 0) {
+        if (g_tier != 2) rc = lu_small_launch(d, 32, 32, dA_array, ipiv_array, info_array, 0, nullptr, 0, cnt[0], lists, s);
+        else rc = lu_blocked_launch(d, 32, 32, dA_array, ipiv_array, info_array, cnt[0], lists, recs, s);
+    }
+    static const int cap[3] = {64, 96, 128};
+    for (int c = 1; c <= 3 && rc == 0; ++c)
+        if (cnt[c] > 0)
+            rc = lu_mid_launch(d, imin(max_m, cap[c - 1]), imin(max_n, cap[c - 1]), dA_array, ipiv_array, info_array,
+                               cnt[c], lists + (size_t)c * batch, s);
+    if (rc == 0 && cnt[4] > 0)
+        rc = lu_blocked_launch(d, max_m, max_n, dA_array, ipiv_array, info_array, cnt[4], lists + 4 * (size_t)batch, recs, s);
     return rc;
 }
 
@@ -278,7 +281,7 @@ magma_int_t magma_dgetrf_vbatched_max_nocheck_work(magma_int_t *m, magma_int_t *
         return -12;
     }
     if (batchCount <= 0 || max_m == 0 || max_n == 0) return 0;
-    return vbatched_run(m, n, max_m, max_n, dA_array, ldda, dipiv_array, info_array, work, batchCount, queue, -1, -1);
+    return vbatched_run(m, n, max_m, max_n, dA_array, ldda, dipiv_array, info_array, work, batchCount, queue, nullptr);
 }
 
 magma_int_t magma_dgetrf_vbatched_max_nocheck(magma_int_t *m, magma_int_t *n, magma_int_t *minmn, magma_int_t max_m,
@@ -294,7 +297,7 @@ magma_int_t magma_dgetrf_vbatched_max_nocheck(magma_int_t *m, magma_int_t *n, ma
         magma_xerbla(__func__, -MAGMA_ERR_DEVICE_ALLOC);
         return MAGMA_ERR_DEVICE_ALLOC;
     }
-    return vbatched_run(m, n, max_m, max_n, dA_array, ldda, ipiv_array, info_array, work, batchCount, queue, -1, -1);
+    return vbatched_run(m, n, max_m, max_n, dA_array, ldda, ipiv_array, info_array, work, batchCount, queue, nullptr);
 }
 
 magma_int_t magma_dgetrf_vbatched(magma_int_t *m, magma_int_t *n, double **dA_array, magma_int_t *ldda,
@@ -307,15 +310,15 @@ magma_int_t magma_dgetrf_vbatched(magma_int_t *m, magma_int_t *n, double **dA_ar
     }
     if (batchCount == 0) return 0;
     // one statistics kernel + one D2H read (the reference: checker kernel + read, setup kernel + read)
-    char *scr = (char *)queue_dscratch(queue, vbatched_work_bytes(batchCount) + 64);
+    char *scr = (char *)queue_dscratch(queue, vbatched_work_bytes(batchCount) + 64);  // 64: the statistics block
     if (!scr) {
         magma_xerbla(__func__, -MAGMA_ERR_DEVICE_ALLOC);
         return MAGMA_ERR_DEVICE_ALLOC;
     }
-    int *stats = (int *)scr;  // 8 ints, then the partition workspace
+    int *stats = (int *)scr;  // 16 ints, then the partition workspace
     void *work = scr + 64;
     vbatched_stats_launch(m, n, ldda, batchCount, stats, queue->stream);
-    int h[8];
+    int h[16];
     cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, queue->stream);
     cudaStreamSynchronize(queue->stream);
     if (h[4] != 0) {
@@ -328,8 +331,15 @@ magma_int_t magma_dgetrf_vbatched(magma_int_t *m, magma_int_t *n, double **dA_ar
         cudaMemsetAsync(info_array, 0, sizeof(int) * (size_t)batchCount, queue->stream);
         return 0;
     }
+    // bin sizes as the partition kernel will produce them (classes above mid_max fall into the last bin)
+    const int mid_max = (g_tier == 2) ? 32 : g_mid_max;
+    int known[5] = {h[5], h[8], h[9], h[10], 0};
+    if (mid_max < 64) known[1] = 0;
+    if (mid_max < 96) known[2] = 0;
+    if (mid_max < 128) known[3] = 0;
+    known[4] = h[6] - known[0] - known[1] - known[2] - known[3];
     magma_int_t rc = vbatched_run(m, n, max_m, max_n, dA_array, ldda, ipiv_array, info_array, work, batchCount, queue,
-                                  h[5], h[6] - h[5]);
+                                  known);
     // the reference's driver returns after a queue sync (src/zgetrf_vbatched.cpp:392)
     cudaStreamSynchronize(queue->stream);
     return rc;
@@ -415,7 +425,7 @@ void magma_idisplace_pointers(magma_int_t **output_array, magma_int_t **input_ar
 // ---------------------------------------------------------------------------------------------
 // Additions
 // ---------------------------------------------------------------------------------------------
-void magma_b200_set_mid_max(int n) { g_mid_max = n < 32 ? 32 : (n > 128 ? 128 : n); }
+void magma_b200_set_mid_max(int n) { g_mid_max = n >= 128 ? 128 : (n >= 96 ? 96 : (n >= 64 ? 64 : 32)); }
 
 void magma_b200_dlarnv_uniform(magma_int_t *iseed, int64_t n, double *dx, magma_queue_t queue)
 {

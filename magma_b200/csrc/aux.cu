@@ -34,7 +34,7 @@ __global__ void memset_int_kernel(int *p, int v, long n)
 __global__ void vbatched_stats_kernel(const int *__restrict__ m, const int *__restrict__ n,
                                       const int *__restrict__ ldda, long batch, int *out8)
 {
-    int mm = 0, mn_ = 0, mmin = 0, mxn = 0, bad = 0x7fffffff, small = 0, nonempty = 0;
+    int mm = 0, mn_ = 0, mmin = 0, mxn = 0, bad = 0x7fffffff, small = 0, nonempty = 0, c64 = 0, c96 = 0, c128 = 0;
     for (long b = (long)blockIdx.x * blockDim.x + threadIdx.x; b < batch; b += (long)gridDim.x * blockDim.x) {
         const int M = m[b], N = n[b], L = ldda[b];
         if (M < 0) bad = min(bad, 1);
@@ -47,7 +47,11 @@ __global__ void vbatched_stats_kernel(const int *__restrict__ m, const int *__re
         mxn = max(mxn, (int)min(prod, (long long)0x7fffffff));
         if (M > 0 && N > 0) {
             ++nonempty;
-            if (M <= 32 && N <= 32) ++small;
+            const int K = max(M, N);
+            if (K <= 32) ++small;
+            else if (K <= 64) ++c64;
+            else if (K <= 96) ++c96;
+            else if (K <= 128) ++c128;
         }
     }
     const unsigned full = 0xffffffffu;
@@ -58,6 +62,9 @@ __global__ void vbatched_stats_kernel(const int *__restrict__ m, const int *__re
     bad = __reduce_min_sync(full, bad);
     small = __reduce_add_sync(full, small);
     nonempty = __reduce_add_sync(full, nonempty);
+    c64 = __reduce_add_sync(full, c64);
+    c96 = __reduce_add_sync(full, c96);
+    c128 = __reduce_add_sync(full, c128);
     if ((threadIdx.x & 31) == 0) {
         atomicMax(out8 + 0, mm);
         atomicMax(out8 + 1, mn_);
@@ -66,36 +73,38 @@ __global__ void vbatched_stats_kernel(const int *__restrict__ m, const int *__re
         if (bad != 0x7fffffff) atomicMax(out8 + 4, 8 - bad);  // smaller argument index wins
         atomicAdd(out8 + 5, small);
         atomicAdd(out8 + 6, nonempty);
+        atomicAdd(out8 + 8, c64);
+        atomicAdd(out8 + 9, c96);
+        atomicAdd(out8 + 10, c128);
     }
 }
 
-// Index lists: matrices with m,n <= 32 (register tier) and the rest (blocked tier). Order inside a
-// list is arbitrary (atomic cursor); empty matrices are dropped from both.
+// Index lists by size class of max(m, n): 0: <= 32 (register tier), 1: <= 64, 2: <= 96, 3: <= mid_max
+// (register-file tier, one list per kernel shape), 4: the rest (blocked tier). List c lives at
+// lists + c * batch. Order inside a list is arbitrary (atomic cursor); empty matrices are dropped.
 __global__ void vbatched_partition_kernel(const int *__restrict__ m, const int *__restrict__ n, long batch,
-                                          int *idx_small, int *idx_big, int *counts2)
+                                          int *lists, int *counts, int mid_max)
 {
     const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool is_small = false, is_big = false;
+    int cls = -1;
     if (b < batch) {
         const int M = m[b], N = n[b];
         if (M > 0 && N > 0) {
-            is_small = (M <= 32 && N <= 32);
-            is_big = !is_small;
+            const int K = max(M, N);
+            cls = K <= 32 ? 0 : (K > mid_max ? 4 : (K <= 64 ? 1 : (K <= 96 ? 2 : 3)));
         }
     }
     const unsigned full = 0xffffffffu;
-    const unsigned bs = __ballot_sync(full, is_small), bb = __ballot_sync(full, is_big);
     const int lane = threadIdx.x & 31;
-    int base_s = 0, base_b = 0;
-    if (lane == 0) {
-        if (bs) base_s = atomicAdd(counts2 + 0, __popc(bs));
-        if (bb) base_b = atomicAdd(counts2 + 1, __popc(bb));
-    }
-    base_s = __shfl_sync(full, base_s, 0);
-    base_b = __shfl_sync(full, base_b, 0);
     const unsigned lt = (1u << lane) - 1u;
-    if (is_small) idx_small[base_s + __popc(bs & lt)] = (int)b;
-    if (is_big) idx_big[base_b + __popc(bb & lt)] = (int)b;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const unsigned bal = __ballot_sync(full, cls == c);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(counts + c, __popc(bal));
+        base = __shfl_sync(full, base, 0);
+        if (cls == c) lists[(size_t)c * batch + base + __popc(bal & lt)] = (int)b;
+    }
 }
 
 // dlarnv(idist = 1): x_i = a^(i+1) * s mod 2^48 (see oracle/lu_oracle.c). Each thread jumps to its
@@ -207,7 +216,7 @@ void memset_int_launch(int *p, int v, long n, cudaStream_t s)
 
 void vbatched_stats_launch(const int *m, const int *n, const int *ldda, long batch, int *out8, cudaStream_t s)
 {
-    cudaMemsetAsync(out8, 0, 8 * sizeof(int), s);
+    cudaMemsetAsync(out8, 0, 16 * sizeof(int), s);
     if (batch <= 0) return;
     long blocks = (batch + 255) / 256;
     if (blocks > 1184) blocks = 1184;  // 8 x 148 SMs
@@ -216,13 +225,12 @@ void vbatched_stats_launch(const int *m, const int *n, const int *ldda, long bat
     MB200_CHECK_LAUNCH_VOID("vbatched_stats_kernel");
 }
 
-void vbatched_partition_launch(const int *m, const int *n, long batch, int *idx_small, int *idx_big, int *counts2,
+void vbatched_partition_launch(const int *m, const int *n, long batch, int *lists, int *counts, int mid_max,
                                cudaStream_t s)
 {
-    cudaMemsetAsync(counts2, 0, 2 * sizeof(int), s);
+    cudaMemsetAsync(counts, 0, 8 * sizeof(int), s);
     if (batch <= 0) return;
-    vbatched_partition_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, s>>>(m, n, batch, idx_small, idx_big,
-                                                                            counts2);
+    vbatched_partition_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, s>>>(m, n, batch, lists, counts, mid_max);
     count_launch();
     MB200_CHECK_LAUNCH_VOID("vbatched_partition_kernel");
 }

@@ -117,13 +117,13 @@ void set_pointer_launch(void **out, char *base, long elem, long lda, long row, l
 void displace_pointers_launch(void **out, void **in, long elem, long lda, long row, long col,
                               long batch, cudaStream_t s);
 void memset_int_launch(int *p, int v, long n, cudaStream_t s);
-// vbatched statistics: out[0..7] = {max_m, max_n, max_minmn, max_mxn(clamped), first_bad_arg,
-// count_small, count_total_nonempty, 0}
-void vbatched_stats_launch(const int *m, const int *n, const int *ldda, long batch, int *out8,
+// vbatched statistics: out[0..15] = {max_m, max_n, max_minmn, max_mxn(clamped), first_bad_arg,
+// count(max(m,n) <= 32), count_nonempty, 0, count(<= 64), count(<= 96), count(<= 128), ...}
+void vbatched_stats_launch(const int *m, const int *n, const int *ldda, long batch, int *out16,
                            cudaStream_t s);
-// builds index lists: small (m,n<=32) first then the rest; counts in out2
-void vbatched_partition_launch(const int *m, const int *n, long batch, int *idx_small,
-                               int *idx_big, int *counts2, cudaStream_t s);
+// builds five index lists by size class (<= 32, <= 64, <= 96, <= mid_max, rest), list c at lists + c*batch
+void vbatched_partition_launch(const int *m, const int *n, long batch, int *lists, int *counts,
+                               int mid_max, cudaStream_t s);
 void dlarnv_launch(uint64_t seed48, int64_t n, double *dx, cudaStream_t s);
 double fp64_peak_run(int kind, cudaStream_t s);
 double hbm_copy_run(size_t bytes, cudaStream_t s);

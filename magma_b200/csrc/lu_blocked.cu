@@ -543,6 +543,171 @@ gemm_kernel(Dims d, double **__restrict__ dA, int j, int tiles_m, int tiles_n, l
 
 
 // -------------------------------------------------------------------------------------------
+// Trailing update on the FP64 tensor pipe: one 128 x 64 tile of C per CTA, C -= L21 * U12 with
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4). tools/dmma_probe.cu showed on the B200 that this
+// instruction equals the chain c = fma(a0,b0,c); c = fma(a1,b1,c); ... with k increasing, bit for
+// bit, so with A negated the tile receives exactly the canonical updates of oracle/lu_oracle.c.
+// Relative to the DFMA kernel above: 16 DMMA per warp and k-step feed on 8 conflict-free LDS.64
+// (the 4x8 DFMA register tile needs 6 LDS.128 per 32 DFMA), so neither issue slots nor the LSU pipe
+// limit the FP64 pipe. Operands are staged once per tile with cp.async; zero padding beyond the
+// panel width is exact (fma(-0, 0, c) = c).
+// Warp grid 4 x 2, warp tile 32 x 32 = 4 x 4 fragments; lane (g = lane/4, q = lane%4) holds
+// C(8i+g, 8jt+2q) and C(8i+g, 8jt+2q+1).
+// -------------------------------------------------------------------------------------------
+constexpr int DM = 128, DN = 64, DMMA_THREADS = 256;
+
+__device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int KW>  // panel width staged per tile (32 or 64)
+__global__ void __launch_bounds__(DMMA_THREADS, 2)
+gemm_dmma_kernel(Dims d, double **__restrict__ dA, int j, int tiles_m, int tiles_n, long batch,
+                 const int *__restrict__ index_list)
+{
+    constexpr int LDA = DM + 4;  // As[k*LDA + r]: (k, r) -> banks 8(k%4) + 2(r%8) + ..: conflict free
+    constexpr int LDB = KW + 4;  // Bs[c*LDB + k]
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *As = reinterpret_cast<double *>(smem_raw);
+    double *Bs = As + KW * LDA;
+
+    const int tiles = tiles_m * tiles_n;
+    const long slot = blockIdx.x / tiles;
+    const int t = blockIdx.x % tiles;
+    const long b = index_list ? index_list[slot] : slot;
+    if (b < 0) return;
+    int m, n, ld;
+    dims_of(d, b, m, n, ld);
+    const int mn = m < n ? m : n;
+    if (j >= mn) return;
+    const int jb = (mn - j) < KW ? (mn - j) : KW;
+    const int r0 = j + jb + (t % tiles_m) * DM;
+    const int c0 = j + jb + (t / tiles_m) * DN;
+    if (r0 >= m || c0 >= n) return;
+    const int rows = (m - r0) < DM ? (m - r0) : DM;
+    const int cols = (n - c0) < DN ? (n - c0) : DN;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int wr = wid & 3, wc = wid >> 2;
+    double *__restrict__ A = dA[b];
+    const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+
+    // C fragments first (longest latency). Interior tiles take the unguarded path.
+    double acc[4][4][2];
+    const bool full = (rows == DM) && (cols == DN);
+    double *Cb = A + (size_t)(r0 + wr * 32 + g) + (size_t)(c0 + wc * 32 + 2 * q) * ld;  // fragment (0,0)
+    if (full) {
+#pragma unroll
+        for (int jt = 0; jt < 4; ++jt) {
+            const double *cp0 = Cb + (size_t)(8 * jt) * ld;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[i][jt][0] = cp0[8 * i];
+                acc[i][jt][1] = cp0[8 * i + ld];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int jt = 0; jt < 4; ++jt) {
+            const int c = wc * 32 + 8 * jt + 2 * q;
+            const double *cp0 = Cb + (size_t)(8 * jt) * ld;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool rok = (wr * 32 + 8 * i + g) < rows;
+                acc[i][jt][0] = (rok && c < cols) ? cp0[8 * i] : 0.0;
+                acc[i][jt][1] = (rok && c + 1 < cols) ? cp0[8 * i + ld] : 0.0;
+            }
+        }
+    }
+    // operands: L21 (rows x jb) -> As[k][r], U12 (jb x cols) -> Bs[c][k]; zero fill outside
+    const double *__restrict__ L21 = A + (size_t)j * ld;  // column j, absolute rows
+    const double *__restrict__ U12 = A + (size_t)j;       // row j, absolute columns
+    if (vec_ok && (r0 & 1) == 0) {
+        for (int idx = tid; idx < KW * DM / 2; idx += DMMA_THREADS) {
+            const int r = (idx % (DM / 2)) * 2, k = idx / (DM / 2);
+            const double *src = &L21[(size_t)(r0 + r) + (size_t)k * ld];
+            if (r + 1 < rows && k < jb) {
+                cp_async16(&As[k * LDA + r], src, true);
+            } else {
+                const bool ok1 = (r < rows) && (k < jb);
+                cp_async8(&As[k * LDA + r], ok1 ? src : A, ok1);
+                cp_async8(&As[k * LDA + r + 1], A, false);
+            }
+        }
+    } else {
+        for (int idx = tid; idx < KW * DM; idx += DMMA_THREADS) {
+            const int r = idx % DM, k = idx / DM;
+            const bool ok = (r < rows) && (k < jb);
+            cp_async8(&As[k * LDA + r], ok ? &L21[(size_t)(r0 + r) + (size_t)k * ld] : A, ok);
+        }
+    }
+    if (vec_ok && (j & 1) == 0) {
+        for (int idx = tid; idx < KW * DN / 2; idx += DMMA_THREADS) {
+            const int k = (idx % (KW / 2)) * 2, c = idx / (KW / 2);
+            const double *src = &U12[(size_t)k + (size_t)(c0 + c) * ld];
+            if (k + 1 < jb && c < cols) {
+                cp_async16(&Bs[c * LDB + k], src, true);
+            } else {
+                const bool ok1 = (k < jb) && (c < cols);
+                cp_async8(&Bs[c * LDB + k], ok1 ? src : A, ok1);
+                cp_async8(&Bs[c * LDB + k + 1], A, false);
+            }
+        }
+    } else {
+        for (int idx = tid; idx < KW * DN; idx += DMMA_THREADS) {
+            const int k = idx % KW, c = idx / KW;
+            const bool ok = (k < jb) && (c < cols);
+            cp_async8(&Bs[c * LDB + k], ok ? &U12[(size_t)k + (size_t)(c0 + c) * ld] : A, ok);
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    const int ksteps = (jb + 3) / 4;
+    const double *Ap = As + q * LDA + wr * 32 + g;          // + ks*4*LDA + 8*i
+    const double *Bp = Bs + (wc * 32 + g) * LDB + q;        // + 8*jt*LDB + ks*4
+#pragma unroll 2
+    for (int ks = 0; ks < ksteps; ++ks) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) af[i] = -Ap[ks * 4 * LDA + 8 * i];
+#pragma unroll
+        for (int jt = 0; jt < 4; ++jt) bf[jt] = Bp[8 * jt * LDB + ks * 4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jt = 0; jt < 4; ++jt) dmma_884(acc[i][jt][0], acc[i][jt][1], af[i], bf[jt]);
+    }
+
+    if (full) {
+#pragma unroll
+        for (int jt = 0; jt < 4; ++jt) {
+            double *cp0 = Cb + (size_t)(8 * jt) * ld;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                cp0[8 * i] = acc[i][jt][0];
+                cp0[8 * i + ld] = acc[i][jt][1];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int jt = 0; jt < 4; ++jt) {
+            const int c = wc * 32 + 8 * jt + 2 * q;
+            double *cp0 = Cb + (size_t)(8 * jt) * ld;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool rok = (wr * 32 + 8 * i + g) < rows;
+                if (rok && c < cols) cp0[8 * i] = acc[i][jt][0];
+                if (rok && c + 1 < cols) cp0[8 * i + ld] = acc[i][jt][1];
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
 // Strip-resident update (panels at most 128 rows tall): one CTA per (matrix, 64-column strip).
 // The whole strip -- block row and every row below it -- is brought into shared memory with
 // coalesced full-column loads, the step's interchanges are applied there (no 8-byte scattered
@@ -853,12 +1018,28 @@ magma_int_t run_step(const Dims &d, int max_m, int max_n, double **dA, int **dip
         MB200_CHECK_LAUNCH("swap_trsm_kernel");
     }
     if (mbelow_max > 0 && nright_max > 0) {
-        const int tiles_m = (mbelow_max + GM - 1) / GM, tiles_n = (nright_max + GN - 1) / GN;
-        const long grid = (long)tiles_m * tiles_n * batch;
-        if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
-        gemm_kernel<W><<<(unsigned)grid, GEMM_THREADS, 0, s>>>(d, dA, j, tiles_m, tiles_n, batch, il);
-        count_launch();
-        MB200_CHECK_LAUNCH("gemm_kernel");
+        if (W == 32 && g_tier != 4) {  // FP64 tensor pipe (tier 4 forces the DFMA kernel, for A/B runs)
+            constexpr int KW = 32;
+            const size_t smem = sizeof(double) * ((size_t)KW * (DM + 4) + (size_t)DN * (KW + 4));
+            static bool attr_set2 = false;
+            if (!attr_set2) {
+                cudaFuncSetAttribute(gemm_dmma_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_set2 = true;
+            }
+            const int tiles_m = (mbelow_max + DM - 1) / DM, tiles_n = (nright_max + DN - 1) / DN;
+            const long grid = (long)tiles_m * tiles_n * batch;
+            if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
+            gemm_dmma_kernel<KW><<<(unsigned)grid, DMMA_THREADS, smem, s>>>(d, dA, j, tiles_m, tiles_n, batch, il);
+            count_launch();
+            MB200_CHECK_LAUNCH("gemm_dmma_kernel");
+        } else {
+            const int tiles_m = (mbelow_max + GM - 1) / GM, tiles_n = (nright_max + GN - 1) / GN;
+            const long grid = (long)tiles_m * tiles_n * batch;
+            if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
+            gemm_kernel<W><<<(unsigned)grid, GEMM_THREADS, 0, s>>>(d, dA, j, tiles_m, tiles_n, batch, il);
+            count_launch();
+            MB200_CHECK_LAUNCH("gemm_kernel");
+        }
     }
     return 0;
 }

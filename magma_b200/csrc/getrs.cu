@@ -189,6 +189,237 @@ getrs_kernel(int trans, int n, int nrhs, int tr_max, double **__restrict__ dA, i
     }
 }
 
+// -------------------------------------------------------------------------------------------
+// getrs, NoTrans, on the FP64 tensor pipe: the right-hand-side tile (n x 16) lives in REGISTERS for
+// the whole call, as DMMA accumulator fragments (warp w owns rows [64w, 64w+64): 8 row tiles x 2
+// column tiles). Per 32-row block: the block's rows go to shared memory, are solved against the
+// diagonal block (staged with cp.async one block ahead; lane = row, one shuffle per unknown), and
+// every other row tile receives C -= A_tile * X_blk as mma.sync.m8n8k4.f64 with the A fragments
+// loaded straight from global memory (each element of L and U is read exactly once, full sectors).
+// DMMA equals the FMA chain in fragment order (tools/dmma_probe.cu), and the backward sweep feeds
+// the fragments in reversed k, so every unknown sees the canonical update order of
+// oracle/lu_oracle.c: bit-identical results. The DFMA kernel above re-read its tile from shared
+// memory per block and waited on dependent global loads inside the update loop (7.4 ms for 4000
+// systems of n = 512, nrhs = 16; reference 5.1 ms).
+// -------------------------------------------------------------------------------------------
+constexpr int XW = 20;  // Xs[k*XW + c]: B-fragment reads (4 rows x 8 columns) are conflict free
+
+__device__ __forceinline__ void dmma_884s(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async8_s(void *smem, const void *gmem, bool pred)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = pred ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gmem), "r"(sz) : "memory");
+}
+
+// diagonal block kb -> Ts[k*32 + i] = A(kb+i, kb+k), zero outside the matrix
+__device__ __forceinline__ void stage_diag(double *Ts, const double *__restrict__ A, int ld, int n, int kb)
+{
+    for (int idx = threadIdx.x; idx < 1024; idx += SOLVE_THREADS) {
+        const int i = idx & 31, k = idx >> 5;
+        const bool ok = (kb + i < n) && (kb + k < n);
+        cp_async8_s(&Ts[idx], ok ? &A[(size_t)(kb + i) + (size_t)(kb + k) * ld] : A, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// perm[i] = original row that LAPACK's forward interchanges leave at position i, computed by
+// tracing every position backwards through the interchanges (n independent traces, no serial pass)
+__device__ void build_perm_par(int n, const int *__restrict__ ipiv, int *perm, int *sipiv)
+{
+    for (int i = threadIdx.x; i < n; i += SOLVE_THREADS) sipiv[i] = ipiv[i] - 1;
+    __syncthreads();
+    for (int i0 = threadIdx.x; i0 < n; i0 += 2 * SOLVE_THREADS) {
+        int c0 = i0, c1 = i0 + SOLVE_THREADS;
+        for (int k = n - 1; k >= 0; --k) {
+            const int p = sipiv[k];
+            c0 = (c0 == k) ? p : ((c0 == p) ? k : c0);
+            c1 = (c1 == k) ? p : ((c1 == p) ? k : c1);
+        }
+        perm[i0] = c0;
+        if (i0 + SOLVE_THREADS < n) perm[i0 + SOLVE_THREADS] = c1;
+    }
+    __syncthreads();
+}
+
+// Row tiles (8 rows) are dealt to the warps round robin: tile t = 8 i + w is local tile i of warp w, so
+// the rows still to be updated are spread evenly over the warps at every block step. Block blk (32 rows) =
+// tiles 4 blk .. 4 blk + 3 = local tile blk / 2 of warps 4 (blk & 1) .. 4 (blk & 1) + 3.
+template <bool fwd, int RT>
+__device__ __forceinline__ void getrs_sweep(double (&acc)[RT][2][2], double *Xs, double *Ts, const double *__restrict__ A,
+                                            int ld, int n, int nblk, int w, int lane, int g, int q)
+{
+#pragma unroll 1
+    for (int bi = 0; bi < nblk; ++bi) {
+        const int blk = fwd ? bi : (nblk - 1 - bi);
+        const int ib = blk >> 1, par = blk & 1;  // the block's rows: local tile ib of warps 4 par .. 4 par + 3
+        const int kb = 32 * blk;
+        const int seq = fwd ? blk : (2 * nblk - 1 - blk);  // position in the overall block sequence
+        double *Tc = Ts + (seq & 1) * 1024;
+        const bool owner = (w >> 2) == par;
+        double *xrow = Xs + (8 * (w & 3) + g) * XW + 2 * q;
+        // ---- the block's rows -> shared memory (acc is indexed statically: uniform switch) ---------------
+        if (owner) {
+#pragma unroll
+            for (int i = 0; i < RT; ++i)
+                if (i == ib) {
+#pragma unroll
+                    for (int jt = 0; jt < 2; ++jt) {
+                        xrow[8 * jt] = acc[i][jt][0];
+                        xrow[8 * jt + 1] = acc[i][jt][1];
+                    }
+                }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        // next diagonal block in flight while this one is used (the turn reuses the last block)
+        {
+            const int nseq = seq + 1;
+            if (nseq < 2 * nblk) {
+                const int nb2 = nseq < nblk ? nseq : (2 * nblk - 1 - nseq);
+                stage_diag(Ts + (nseq & 1) * 1024, A, ld, n, 32 * nb2);
+            }
+        }
+        // ---- diagonal block: warp per two right-hand sides, lane = row -----------------------------
+        {
+            const int ca = 2 * w, cb2 = 2 * w + 1;
+            double xa = Xs[lane * XW + ca], xb = Xs[lane * XW + cb2];
+            if (fwd) {
+#pragma unroll 8
+                for (int k = 0; k < 32; ++k) {
+                    const double t = (lane > k) ? Tc[k * 32 + lane] : 0.0;
+                    const double ka = __shfl_sync(0xffffffffu, xa, k), kb2 = __shfl_sync(0xffffffffu, xb, k);
+                    xa = fma(-t, ka, xa);
+                    xb = fma(-t, kb2, xb);
+                }
+            } else {
+                const double dg = Tc[lane * 32 + lane];
+                const double dinv = (kb + lane < n) ? 1.0 / dg : 0.0;
+#pragma unroll 8
+                for (int kk = 0; kk < 32; ++kk) {
+                    const int k = 31 - kk;
+                    const double t = (lane < k) ? Tc[k * 32 + lane] : 0.0;
+                    if (lane == k) {
+                        xa = xa * dinv;
+                        xb = xb * dinv;
+                    }
+                    const double ka = __shfl_sync(0xffffffffu, xa, k), kb2 = __shfl_sync(0xffffffffu, xb, k);
+                    xa = fma(-t, ka, xa);
+                    xb = fma(-t, kb2, xb);
+                }
+            }
+            Xs[lane * XW + ca] = xa;
+            Xs[lane * XW + cb2] = xb;
+        }
+        __syncthreads();
+        // ---- solved rows back to their owner ---------------------------------------------------------------
+        if (owner) {
+#pragma unroll
+            for (int i = 0; i < RT; ++i)
+                if (i == ib) {
+#pragma unroll
+                    for (int jt = 0; jt < 2; ++jt) {
+                        acc[i][jt][0] = xrow[8 * jt];
+                        acc[i][jt][1] = xrow[8 * jt + 1];
+                    }
+                }
+        }
+        // ---- every other row of this sweep: C -= A_tile * X_blk. A fragments of local tile i: rows
+        //      8 (8 i + w) + g, columns kb + k(ks, q); loaded one tile ahead of their use ------------------------
+        double af[2][8];
+        auto load_tile = [&](int i, double (&dst)[8]) {
+            const int t = 8 * i + w;
+            const bool todo = fwd ? (t >= 4 * blk + 4) : (t < 4 * blk);
+            const int r = 8 * t + g;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const int k = fwd ? (4 * ks + q) : (31 - (4 * ks + q));
+                dst[ks] = (todo && r < n && kb + k < n) ? A[(size_t)r + (size_t)(kb + k) * ld] : 0.0;
+            }
+        };
+        load_tile(0, af[0]);
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            if (i + 1 < RT) load_tile(i + 1, af[(i + 1) & 1]);
+            const int t = 8 * i + w;
+            const bool todo = fwd ? (t >= 4 * blk + 4) : (t < 4 * blk);
+            if (todo && 8 * t < n) {  // warp-uniform
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const int k = fwd ? (4 * ks + q) : (31 - (4 * ks + q));
+                    const double na = -af[i & 1][ks];
+#pragma unroll
+                    for (int jt = 0; jt < 2; ++jt) dmma_884s(acc[i][jt][0], acc[i][jt][1], na, Xs[k * XW + 8 * jt + g]);
+                }
+            }
+        }
+        __syncthreads();  // Xs is rewritten by the next block
+    }
+}
+
+template <int RT>  // row tiles (8 rows) per warp: n <= 64 * RT
+__global__ void __launch_bounds__(SOLVE_THREADS, 2)
+getrs_dmma_kernel(int n, int nrhs, double **__restrict__ dA, int ldda, int **__restrict__ dipiv,
+                  double **__restrict__ dB, int lddb, int rhs_tiles)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *Xs = reinterpret_cast<double *>(smem_raw);  // [32][XW]
+    double *Ts = Xs + 32 * XW;                           // [2][32*32]
+    int *perm = reinterpret_cast<int *>(Ts + 2 * 1024);
+    int *sipiv = perm + n;
+
+    const long b = blockIdx.x / rhs_tiles;
+    const int tile = blockIdx.x % rhs_tiles;
+    const int c0 = tile * 16;
+    const int tr = (nrhs - c0) < 16 ? (nrhs - c0) : 16;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int g = lane >> 2, q = lane & 3;
+    const double *__restrict__ A = dA[b];
+    double *__restrict__ B = dB[b] + (size_t)c0 * lddb;
+    const int ld = ldda;
+    const int nblk = (n + 31) / 32;
+
+    stage_diag(Ts, A, ld, n, 0);
+    build_perm_par(n, dipiv[b], perm, sipiv);
+
+    // right-hand sides -> accumulator fragments, interchanges applied on the way in
+    double acc[RT][2][2];
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+        const int r = 8 * (8 * i + w) + g;
+        const int pr = (r < n) ? perm[r] : 0;
+#pragma unroll
+        for (int jt = 0; jt < 2; ++jt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = 8 * jt + 2 * q + e;
+                acc[i][jt][e] = (r < n && c < tr) ? B[pr + (size_t)c * lddb] : 0.0;
+            }
+    }
+
+    // L y = P b (unit lower, blocks ascending), then U x = y (blocks descending)
+    getrs_sweep<true, RT>(acc, Xs, Ts, A, ld, n, nblk, w, lane, g, q);
+    getrs_sweep<false, RT>(acc, Xs, Ts, A, ld, n, nblk, w, lane, g, q);
+
+#pragma unroll
+    for (int i = 0; i < RT; ++i) {
+        const int r = 8 * (8 * i + w) + g;
+#pragma unroll
+        for (int jt = 0; jt < 2; ++jt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = 8 * jt + 2 * q + e;
+                if (r < n && c < tr) B[r + (size_t)c * lddb] = acc[i][jt][e];
+            }
+    }
+}
+
 // standalone trsm, side = Left.  B <- alpha * op(A)^-1 B
 __global__ void __launch_bounds__(SOLVE_THREADS, 2)
 trsm_left_kernel(int uplo, int trans, int diag, int n, int nrhs, int tr_max, double alpha,
@@ -306,6 +537,19 @@ int pick_tr(int n, int nrhs, size_t &smem)
 magma_int_t getrs_launch(int trans, int n, int nrhs, double **dA, int ldda, int **dipiv, double **dB, int lddb,
                          long batch, cudaStream_t s)
 {
+    if (trans == MagmaNoTrans && n > 32 && n <= 512 && g_tier != 4) {  // tier 4: DFMA kernels only (A/B runs)
+        const int rhs_tiles = (nrhs + 15) / 16;
+        const long grid = batch * rhs_tiles;
+        if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
+        const size_t smem = sizeof(double) * (32 * XW + 2 * 1024) + sizeof(int) * 2 * (size_t)n;
+        if (n <= 256)
+            getrs_dmma_kernel<4><<<(unsigned)grid, SOLVE_THREADS, smem, s>>>(n, nrhs, dA, ldda, dipiv, dB, lddb, rhs_tiles);
+        else
+            getrs_dmma_kernel<8><<<(unsigned)grid, SOLVE_THREADS, smem, s>>>(n, nrhs, dA, ldda, dipiv, dB, lddb, rhs_tiles);
+        count_launch();
+        MB200_CHECK_LAUNCH("getrs_dmma_kernel");
+        return 0;
+    }
     size_t smem;
     const int tr = pick_tr(n, nrhs, smem);
     if (tr == 0) return MAGMA_ERR_NOT_SUPPORTED;

@@ -303,8 +303,11 @@ constexpr int TNP = TN + 1;
 template <int W>
 __global__ void __launch_bounds__(ST_THREADS)
 swap_trsm_kernel(Dims d, double **__restrict__ dA, const PivRec *__restrict__ recs, int j, int right_tiles,
-                 int left_tiles, long batch, const int *__restrict__ index_list)
+                 int left_tiles, int left_begin, int pre_k0, long batch, const int *__restrict__ index_list)
 {
+    // left tiles cover columns [left_begin, j). pre_k0 >= 0: this step's trailing update by the 32 columns
+    // at pre_k0 was postponed (64-wide pairing, lu_blocked_launch): the block row gets it here, after the
+    // interchanges and before the triangular solve, so every element still sees k increasing.
     __shared__ double T0[KB * TNP];       // original top rows   [k*TNP + c]
     __shared__ double Bs[KB * TNP];       // permuted top block  [p*TNP + c]
     __shared__ double Ls[KB * (KB + 1)];  // L11                 [i*(KB+1) + k]
@@ -328,7 +331,7 @@ swap_trsm_kernel(Dims d, double **__restrict__ dA, const PivRec *__restrict__ re
         c1 = c0 + TN < n ? c0 + TN : n;
     } else {
         right = false;
-        c0 = (tile - right_tiles) * TN;
+        c0 = left_begin + (tile - right_tiles) * TN;
         c1 = c0 + TN < j ? c0 + TN : j;
     }
     if (c0 >= c1) return;
@@ -377,6 +380,53 @@ swap_trsm_kernel(Dims d, double **__restrict__ dA, const PivRec *__restrict__ re
             if (k < jb && c < wt && s_top[k] != k) Ap[k + (size_t)(c0 + c) * ld] = Bs[k * TNP + c];
         }
         return;
+    }
+    if (pre_k0 >= 0) {
+        // postponed update of the block row: Bs(i, c) -= sum_k A(j+i, pre_k0+k) * A(pre_k0+k, c0+c), k increasing.
+        // T0 is free now: it takes U(pre_k0.., tile) (k fast); Lp goes where L11 will be loaded afterwards.
+        // (Prefetching all of this with cp.async into separate buffers at kernel start was slower: 67 KB of
+        // shared memory per CTA cost a quarter of the occupancy.)
+        __syncthreads();
+        double *Lp = Ls;  // [i*(KB+1) + k]
+        for (int idx = tid; idx < KB * KB; idx += ST_THREADS) {
+            const int i = idx & 31, k = idx >> 5;
+            Lp[i * (KB + 1) + k] = (i < jb) ? Ap[i + (size_t)(pre_k0 + k) * ld] : 0.0;
+        }
+#pragma unroll 4
+        for (int idx = tid; idx < KB * TN; idx += ST_THREADS) {
+            const int k = idx & 31, c = idx >> 5;
+            if (c < wt) T0[k * TNP + c] = A[(size_t)(pre_k0 + k) + (size_t)(c0 + c) * ld];
+        }
+        __syncthreads();
+        {
+            const int col = tid & (TN - 1), half = tid >> 6;  // 64 columns x 2 halves of the 32 rows
+            if (col < wt) {
+#pragma unroll 1
+                for (int i = half * 16; i < half * 16 + 16; i += 4) {
+                    double x0 = Bs[i * TNP + col], x1 = Bs[(i + 1) * TNP + col], x2 = Bs[(i + 2) * TNP + col],
+                           x3 = Bs[(i + 3) * TNP + col];
+#pragma unroll 8
+                    for (int k = 0; k < KB; ++k) {
+                        const double u = T0[k * TNP + col];
+                        x0 = fma(-Lp[i * (KB + 1) + k], u, x0);
+                        x1 = fma(-Lp[(i + 1) * (KB + 1) + k], u, x1);
+                        x2 = fma(-Lp[(i + 2) * (KB + 1) + k], u, x2);
+                        x3 = fma(-Lp[(i + 3) * (KB + 1) + k], u, x3);
+                    }
+                    if (i < jb) Bs[i * TNP + col] = x0;
+                    if (i + 1 < jb) Bs[(i + 1) * TNP + col] = x1;
+                    if (i + 2 < jb) Bs[(i + 2) * TNP + col] = x2;
+                    if (i + 3 < jb) Bs[(i + 3) * TNP + col] = x3;
+                }
+            }
+        }
+        __syncthreads();
+        // now L11 of this step
+        for (int idx = tid; idx < KB * KB; idx += ST_THREADS) {
+            const int i = idx & 31, k = idx >> 5;
+            if (i < jb && k < jb) Ls[i * (KB + 1) + k] = Ap[i + (size_t)(j + k) * ld];
+        }
+        __syncthreads();
     }
     // U12 = L11^-1 * Bs: one thread per column, canonical order
     if (tid < wt) {
@@ -562,10 +612,11 @@ __device__ __forceinline__ void dmma_884(double &c0, double &c1, double a, doubl
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <int KW>  // panel width staged per tile (32 or 64)
+// Region form: C[rs.., cs..climit) -= A[rs.., k0..k0+kw) * A[k0..k0+kw, cs..climit), kw = min(KW, min(m,n) - k0).
+template <int KW>  // widest k range staged per tile (32 or 64)
 __global__ void __launch_bounds__(DMMA_THREADS, 2)
-gemm_dmma_kernel(Dims d, double **__restrict__ dA, int j, int tiles_m, int tiles_n, long batch,
-                 const int *__restrict__ index_list)
+gemm_dmma_kernel(Dims d, double **__restrict__ dA, int k0, int rs, int cs, int climit, int tiles_m, int tiles_n,
+                 long batch, const int *__restrict__ index_list)
 {
     constexpr int LDA = DM + 4;  // As[k*LDA + r]: (k, r) -> banks 8(k%4) + 2(r%8) + ..: conflict free
     constexpr int LDB = KW + 4;  // Bs[c*LDB + k]
@@ -581,13 +632,15 @@ gemm_dmma_kernel(Dims d, double **__restrict__ dA, int j, int tiles_m, int tiles
     int m, n, ld;
     dims_of(d, b, m, n, ld);
     const int mn = m < n ? m : n;
+    const int j = k0;
     if (j >= mn) return;
     const int jb = (mn - j) < KW ? (mn - j) : KW;
-    const int r0 = j + jb + (t % tiles_m) * DM;
-    const int c0 = j + jb + (t / tiles_m) * DN;
-    if (r0 >= m || c0 >= n) return;
+    const int r0 = rs + (t % tiles_m) * DM;
+    const int c0 = cs + (t / tiles_m) * DN;
+    const int nlim = n < climit ? n : climit;
+    if (r0 >= m || c0 >= nlim) return;
     const int rows = (m - r0) < DM ? (m - r0) : DM;
-    const int cols = (n - c0) < DN ? (n - c0) : DN;
+    const int cols = (nlim - c0) < DN ? (nlim - c0) : DN;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -902,8 +955,10 @@ constexpr int LSWP_COLS = 4;  // columns staged per round
 
 __global__ void __launch_bounds__(LSWP_THREADS)
 laswp_left_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int blocks, int max_rows, int step,
-                  long batch, const int *__restrict__ index_list)
+                  int pair_end_block, long batch, const int *__restrict__ index_list)
 {
+    // blocks J < pair_end_block with J even were factored as the first half of a 64-wide pair: the second
+    // half's interchanges were applied to them on the spot, the deferred pass starts one panel later
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int *perm = reinterpret_cast<int *>(smem_raw);                                   // [max_rows]
     int *spiv = perm + max_rows;                                                     // [max_rows]
@@ -917,8 +972,9 @@ laswp_left_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, in
     int m, n, ld;
     dims_of(d, b, m, n, ld);
     const int mn = m < n ? m : n;
-    const int r0 = (J + 1) * step;   // first row touched; columns J*step .. r0-1
-    if (r0 >= mn) return;            // no later panel
+    const bool paired = (J < pair_end_block) && ((J & 1) == 0);
+    const int r0 = (J + (paired ? 2 : 1)) * step;  // first row touched
+    if (r0 >= mn) return;                          // no later panel
     const int rows = m - r0;
     const int tid = threadIdx.x;
     double *__restrict__ A = dA[b];
@@ -944,7 +1000,7 @@ laswp_left_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, in
     }
     __syncthreads();
     if (!spiv[0]) return;
-    const int cbeg = J * step, cend = r0;  // r0 <= mn <= n
+    const int cbeg = J * step, cend = (J + 1) * step;  // the block's own columns
     for (int cb = cbeg; cb < cend; cb += LSWP_COLS) {
         const int nc = (cend - cb) < LSWP_COLS ? (cend - cb) : LSWP_COLS;
         for (int c = 0; c < nc; ++c) {
@@ -961,6 +1017,69 @@ laswp_left_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, in
         }
         __syncthreads();
     }
+}
+
+// C[rs.., cs..climit) -= A[:, k0..k0+KW) * A[k0..k0+KW, :) over at most rows_max x cols_max per matrix
+template <int KW>
+magma_int_t launch_gemm_dmma(const Dims &d, double **dA, int k0, int rs, int cs, int climit, int rows_max, int cols_max,
+                             long batch, const int *il, cudaStream_t s)
+{
+    if (rows_max <= 0 || cols_max <= 0) return 0;
+    const size_t smem = sizeof(double) * ((size_t)KW * (DM + 4) + (size_t)DN * (KW + 4));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(gemm_dmma_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    const int tiles_m = (rows_max + DM - 1) / DM, tiles_n = (cols_max + DN - 1) / DN;
+    const long grid = (long)tiles_m * tiles_n * batch;
+    if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
+    gemm_dmma_kernel<KW><<<(unsigned)grid, DMMA_THREADS, smem, s>>>(d, dA, k0, rs, cs, climit, tiles_m, tiles_n, batch, il);
+    count_launch();
+    MB200_CHECK_LAUNCH("gemm_dmma_kernel");
+    return 0;
+}
+
+// Two 32-column panels as one 64-wide step (panels <= 512 rows, both in the tiled regime). The trailing
+// matrix is read and written ONCE per 64 columns instead of once per 32 (the k = 32 update was HBM bound:
+// 87 GB per n = 512 call):
+//   panel(j); interchanges + U12a for every column right of it; k = 32 update of the NEXT panel's columns only;
+//   panel(j+32); its interchanges applied to the first panel's columns on the spot (so L21 of both panels is in
+//   the same row order); interchanges + postponed k = j..j+31 update of the block row + U12b for the columns
+//   right of j+64; one k = 64 update of everything below and right of j+64.
+// Per element the updates still arrive with k increasing: bit-identical to the 32-wide flow.
+magma_int_t run_pair(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo, PivRec *recs, int j,
+                     long batch, const int *il, cudaStream_t s)
+{
+    const int j2 = j + 32;
+    auto panel = [&](int jj) -> magma_int_t {
+        int T = ((max_m - jj + 31) / 32) * 32;
+        if (T > 512) return MAGMA_ERR_NOT_SUPPORTED;
+        panel_kernel<1, 32><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, jj, batch, il);
+        count_launch();
+        MB200_CHECK_LAUNCH("panel_kernel");
+        return 0;
+    };
+    auto swap_trsm = [&](int jj, int right_tiles, int left_tiles, int left_begin, int pre_k0) -> magma_int_t {
+        const long grid = (long)(right_tiles + left_tiles) * batch;
+        if (grid <= 0) return 0;
+        if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
+        swap_trsm_kernel<32><<<(unsigned)grid, ST_THREADS, 0, s>>>(d, dA, recs, jj, right_tiles, left_tiles, left_begin, pre_k0,
+                                                                   batch, il);
+        count_launch();
+        MB200_CHECK_LAUNCH("swap_trsm_kernel");
+        return 0;
+    };
+    magma_int_t rc;
+    const int nright1 = d.vm ? (max_n - j - 1) : (max_n - j - 32);
+    const int nright2 = d.vm ? (max_n - j2 - 1) : (max_n - j2 - 32);
+    if ((rc = panel(j)) != 0) return rc;
+    if ((rc = swap_trsm(j, nright1 > 0 ? (nright1 + TN - 1) / TN : 0, 0, 0, -1)) != 0) return rc;
+    if ((rc = launch_gemm_dmma<32>(d, dA, j, j2, j2, j2 + 32, max_m - j2, 32, batch, il, s)) != 0) return rc;
+    if ((rc = panel(j2)) != 0) return rc;
+    if ((rc = swap_trsm(j2, 0, 1, j, -1)) != 0) return rc;
+    if ((rc = swap_trsm(j2, nright2 > 0 ? (nright2 + TN - 1) / TN : 0, 0, 0, j)) != 0) return rc;
+    return launch_gemm_dmma<64>(d, dA, j, j2 + 32, j2 + 32, 0x7fffffff, max_m - j2 - 32, max_n - j2 - 32, batch, il, s);
 }
 
 template <int R, int W>
@@ -1003,7 +1122,7 @@ magma_int_t run_step(const Dims &d, int max_m, int max_n, double **dA, int **dip
         count_launch();
         MB200_CHECK_LAUNCH("update_strip_kernel");
         if (left_tiles > 0) {
-            swap_trsm_kernel<W><<<(unsigned)((long)left_tiles * batch), ST_THREADS, 0, s>>>(d, dA, recs, j, 0, left_tiles, batch, il);
+            swap_trsm_kernel<W><<<(unsigned)((long)left_tiles * batch), ST_THREADS, 0, s>>>(d, dA, recs, j, 0, left_tiles, 0, -1, batch, il);
             count_launch();
             MB200_CHECK_LAUNCH("swap_trsm_kernel");
         }
@@ -1013,25 +1132,16 @@ magma_int_t run_step(const Dims &d, int max_m, int max_n, double **dA, int **dip
     {
         const long grid = (long)(right_tiles + left_tiles) * batch;
         if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
-        swap_trsm_kernel<W><<<(unsigned)grid, ST_THREADS, 0, s>>>(d, dA, recs, j, right_tiles, left_tiles, batch, il);
+        swap_trsm_kernel<W><<<(unsigned)grid, ST_THREADS, 0, s>>>(d, dA, recs, j, right_tiles, left_tiles, 0, -1, batch, il);
         count_launch();
         MB200_CHECK_LAUNCH("swap_trsm_kernel");
     }
     if (mbelow_max > 0 && nright_max > 0) {
         if (W == 32 && g_tier != 4) {  // FP64 tensor pipe (tier 4 forces the DFMA kernel, for A/B runs)
-            constexpr int KW = 32;
-            const size_t smem = sizeof(double) * ((size_t)KW * (DM + 4) + (size_t)DN * (KW + 4));
-            static bool attr_set2 = false;
-            if (!attr_set2) {
-                cudaFuncSetAttribute(gemm_dmma_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_set2 = true;
-            }
-            const int tiles_m = (mbelow_max + DM - 1) / DM, tiles_n = (nright_max + DN - 1) / DN;
-            const long grid = (long)tiles_m * tiles_n * batch;
-            if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
-            gemm_dmma_kernel<KW><<<(unsigned)grid, DMMA_THREADS, smem, s>>>(d, dA, j, tiles_m, tiles_n, batch, il);
-            count_launch();
-            MB200_CHECK_LAUNCH("gemm_dmma_kernel");
+            // region rows/cols >= j + 32: a matrix on a narrower (last) panel has nothing left below or to the right
+            const magma_int_t rc = launch_gemm_dmma<32>(d, dA, j, j + 32, j + 32, 0x7fffffff, max_m - j - 32, max_n - j - 32,
+                                                        batch, il, s);
+            if (rc != 0) return rc;
         } else {
             const int tiles_m = (mbelow_max + GM - 1) / GM, tiles_n = (nright_max + GN - 1) / GN;
             const long grid = (long)tiles_m * tiles_n * batch;
@@ -1055,11 +1165,22 @@ magma_int_t lu_blocked_launch(const Dims &d, int max_m, int max_n, double **dA, 
     PivRec *recs = reinterpret_cast<PivRec *>(workspace);
     const int max_mn = max_m < max_n ? max_m : max_n;  // upper bound of min(m_b, n_b)
     const bool defer_left = (max_m <= 512);             // every step is 32 wide
+    int pair_end_block = 0;                              // column blocks < this were factored in 64-wide pairs
     int j = 0;
     while (j < max_mn) {
         const int mp = max_m - j;
         magma_int_t rc;
         int w;
+        // 64-wide pairing: both panels in the register-panel regime, the second one still above the strip
+        // regime, tensor-pipe update available, and nothing to the left of j still waiting for pairing
+        if (defer_left && g_tier != 4 && g_tier != 5 && mp <= 512 && (mp - 32) > SROWS && (j + 32) < max_mn &&
+            j == 32 * pair_end_block) {
+            rc = run_pair(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s);
+            if (rc != 0) return rc;
+            j += 64;
+            pair_end_block += 2;
+            continue;
+        }
         if (mp <= 512)       { w = 32; rc = run_step<1, 32>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left); }
         else if (mp <= 1024) { w = 16; rc = run_step<2, 16>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left); }
         else if (mp <= 2048) { w = 8;  rc = run_step<4, 8>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left); }
@@ -1075,7 +1196,7 @@ magma_int_t lu_blocked_launch(const Dims &d, int max_m, int max_n, double **dA, 
         const size_t smem = sizeof(int) * 2 * (size_t)max_rows + 16 + sizeof(double) * LSWP_COLS * (size_t)max_rows;
         const long grid = (long)blocks * batch;
         if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
-        laswp_left_kernel<<<(unsigned)grid, LSWP_THREADS, smem, s>>>(d, dA, dipiv, blocks, max_rows, 32, batch, index_list);
+        laswp_left_kernel<<<(unsigned)grid, LSWP_THREADS, smem, s>>>(d, dA, dipiv, blocks, max_rows, 32, pair_end_block, batch, index_list);
         count_launch();
         MB200_CHECK_LAUNCH("laswp_left_kernel");
     }

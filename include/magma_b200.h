@@ -300,7 +300,8 @@ double magma_b200_hbm_copy_gbs(size_t bytes, magma_queue_t queue);
 
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t magma_b200_launch_count(void);
-/* Force a tier for tests/benches: 0 = auto, 1 = register/warp (small), 2 = blocked. */
+/* Force a tier for tests/benches: 0 = auto, 1 = register/warp (small), 2 = blocked everywhere,
+ * 4 = blocked tier and getrs on the DFMA kernels only (no tensor pipe), 5 = no 64-wide pairing. */
 void magma_b200_set_tier(int tier);
 /* Largest max(m,n) routed to the register-file tier (lu_mid.cu), 32..128; for tuning sweeps. */
 void magma_b200_set_mid_max(int n);

@@ -1,6 +1,7 @@
 // Host drivers: the magma_v2 batched-LU entry points, argument checks and tier dispatch.
 // Replaces src/z{getrf,getrs,gesv}_batched.cpp, src/zgetrf_vbatched.cpp and the tuning tables in
 // control/get_batched_crossover.cpp / control/get_ntcol.cpp for this path.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -31,6 +32,7 @@ constexpr long MAX_CHUNK = 1L << 24;
 // Largest dimension routed to the register-file tier (lu_mid.cu); above it the blocked tier runs.
 // Measured crossover on B200 (tools/gpu_probe.py, PROBE_MID): see DESIGN.md "tiers and crossovers".
 int g_mid_max = 128;
+int g_host_chunk_mb = 32;  // host front ends: payload per staging buffer (MB200_HOST_CHUNK_MB overrides, for sweeps)
 
 }  // namespace
 
@@ -496,11 +498,16 @@ static magma_int_t host_pipeline(bool solve, int m, int n, int nrhs, double *hA,
                                  int ldb, int *hinfo, long batch, magma_queue_t queue)
 {
     ensure_aux(queue);
+    if (const char *e = getenv("MB200_HOST_CHUNK_MB")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 1024) g_host_chunk_mb = v;
+    }
     const int mn = imin(m, n);
     const size_t a_elems = (size_t)lda * n, b_elems = solve ? (size_t)ldb * nrhs : 0;
     const size_t per_mat = (a_elems + b_elems) * 8 + (size_t)mn * 4 + 4 + 3 * 8;
-    // chunk: ~256 MiB of payload per buffer, at least 1 matrix, two buffers in flight
-    long chunk = (long)std::max<size_t>(1, ((size_t)256 << 20) / per_mat);
+    // chunk: ~32 MiB of payload per buffer (pipeline fill + drain = one chunk each way; 256 MiB chunks cost
+    // ~9 ms of a 52 ms step at PCIe speed), at least 1 matrix, two buffers in flight
+    long chunk = (long)std::max<size_t>(1, ((size_t)g_host_chunk_mb << 20) / per_mat);
     if (chunk > batch) chunk = batch;
     const size_t stride = ((per_mat * chunk + 64 + 255) / 256) * 256;
     char *dev = (char *)queue_dscratch(queue, 2 * stride, 0);

@@ -313,6 +313,9 @@ __device__ __forceinline__ double shfl64(double v, int src)
     return __hiloint2double(hi, lo);
 }
 
+// reciprocal for the cold path: one out-of-line copy instead of a second inlined Newton sequence per step
+__device__ __noinline__ double rcp_cold(double x) { return 1.0 / x; }
+
 // x1 if flag else x0, as a select on registers (written as `flag ? a[1][j] : a[0][j]` nvcc turns the
 // row array into a dynamically indexed local-memory array)
 __device__ __forceinline__ double sel64(unsigned flag, double x1, double x0)
@@ -327,6 +330,8 @@ struct SqsSmem {           // one per matrix in flight (fused-solve variant only
     double stage[N * N];   // factors in final row order, dense column-major
     double y[N];           // right-hand side in final row order
     double dinv[N];        // 1 / u(i,i)
+    double pad[8];         // group stride = 16 banks mod 32: the four groups of a warp read their 64-byte
+                           // column pieces in two wavefronts instead of four (ncu: 60 excess LDS wavefronts/pass)
 };
 
 // WC warps per CTA; LOCK: one CTA-wide barrier per column step keeps the warps of a CTA on the same
@@ -395,7 +400,8 @@ lu_sqs_kernel(double *const *__restrict__ dA, int *const *__restrict__ dipiv, in
         unsigned take1 = h[1] > h[0] ? 1u : 0u;
         const unsigned hm = h[1] > h[0] ? h[1] : h[0];
         double cv = sel64(take1, a[1][i], a[0][i]);  // this lane's candidate
-        double rinv = 1.0 / cv;                 // inverted while the search is in flight
+        double rtrue = 1.0 / cv;                     // inverted while the search is in flight
+        double rinv = (cv != 0.0) ? rtrue : 0.0;     // what is broadcast: a zero pivot travels as zero
         const unsigned mx = gmax<G>(hm);
         unsigned cand = (hm == mx) ? 1u : 0u;
         unsigned bal = __ballot_sync(FULL, cand != 0) & gmask;
@@ -411,16 +417,17 @@ lu_sqs_kernel(double *const *__restrict__ dA, int *const *__restrict__ dipiv, in
             take1 = res >> 1;
             bal = __ballot_sync(FULL, cand != 0) & gmask;
             cv = sel64(take1, a[1][i], a[0][i]);
-            rinv = 1.0 / cv;
+            rtrue = rcp_cold(cv);
+            rinv = (cv != 0.0) ? rtrue : 0.0;
         }
         const int P = 31 - __clz((int)bal);  // the (single) pivot lane of this group
 
         // ---- broadcasts from the pivot lane ------------------------------------------------------------
-        const double piv = shfl64(cv, P);
+        // an exactly zero pivot travels as a zero "reciprocal" (saves the broadcast of the pivot value itself)
         const double rr = shfl64(rinv, P);
         const unsigned p = __shfl_sync(FULL, take1 ? pos[1] : pos[0], P);  // current position of the pivot row
         if (sub == (i % G)) myipiv[i / G] = (int)p + 1;
-        const bool nz = (piv != 0.0);
+        const bool nz = (rr != 0.0);
         if (!nz) zmask |= (1u << i);
         double l[R];
 #pragma unroll
@@ -428,7 +435,7 @@ lu_sqs_kernel(double *const *__restrict__ dA, int *const *__restrict__ dipiv, in
             const bool pv = (cand != 0) && (take1 == (unsigned)r);
             if (pos[r] == (unsigned)i) pos[r] = p;
             if (pv) pos[r] = (unsigned)i;
-            if (NRHS && pv) mydinv[r] = rinv;
+            if (NRHS && pv) mydinv[r] = rtrue;  // the solve divides by the pivot whatever it is, like the oracle
             // rows that are not updated use l = 0 (see lu_sq_kernel)
             const bool upd = nz && pos[r] > (unsigned)i;
             l[r] = upd ? a[r][i] * rr : 0.0;

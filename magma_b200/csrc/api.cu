@@ -32,7 +32,7 @@ constexpr long MAX_CHUNK = 1L << 24;
 // Largest dimension routed to the register-file tier (lu_mid.cu); above it the blocked tier runs.
 // Measured crossover on B200 (tools/gpu_probe.py, PROBE_MID): see DESIGN.md "tiers and crossovers".
 int g_mid_max = 128;
-int g_host_chunk_mb = 32;  // host front ends: payload per staging buffer (MB200_HOST_CHUNK_MB overrides, for sweeps)
+int g_host_chunk_mb = 64;  // host front ends: payload per staging buffer (MB200_HOST_CHUNK_MB overrides, for sweeps)
 
 }  // namespace
 
@@ -505,8 +505,8 @@ static magma_int_t host_pipeline(bool solve, int m, int n, int nrhs, double *hA,
     const int mn = imin(m, n);
     const size_t a_elems = (size_t)lda * n, b_elems = solve ? (size_t)ldb * nrhs : 0;
     const size_t per_mat = (a_elems + b_elems) * 8 + (size_t)mn * 4 + 4 + 3 * 8;
-    // chunk: ~32 MiB of payload per buffer (pipeline fill + drain = one chunk each way; 256 MiB chunks cost
-    // ~9 ms of a 52 ms step at PCIe speed), at least 1 matrix, two buffers in flight
+    // chunk: ~64 MiB of payload per buffer (pipeline fill + drain = one chunk each way; measured 50.0 ms per
+    // headline step at 64 MiB vs 51.9 at 256 MiB and 59 at 8 MiB: PCIe-bound), at least 1 matrix, two buffers
     long chunk = (long)std::max<size_t>(1, ((size_t)g_host_chunk_mb << 20) / per_mat);
     if (chunk > batch) chunk = batch;
     const size_t stride = ((per_mat * chunk + 64 + 255) / 256) * 256;

@@ -218,10 +218,10 @@ magma_int_t magma_dgesv_batched(magma_int_t n, magma_int_t nrhs, double **dA_arr
 }
 
 // ---------------------------------------------------------------------------------------------
-// Variable-size LU. Workspace layout (ints): [ 5 index lists of `batch` | counts (8) ], then the blocked
+// Variable-size LU. Workspace layout (ints): [ 7 index lists of `batch` | counts (8) ], then the blocked
 // tier's pivot records. Matrices are binned by max(m, n) and every bin runs the tier built for it.
 // ---------------------------------------------------------------------------------------------
-static size_t vbatched_lists_bytes(long batch) { return (((size_t)(5 * batch + 8) * sizeof(int)) + 511) & ~(size_t)511; }
+static size_t vbatched_lists_bytes(long batch) { return (((size_t)(7 * batch + 8) * sizeof(int)) + 511) & ~(size_t)511; }
 static size_t vbatched_work_bytes(long batch) { return vbatched_lists_bytes(batch) + lu_blocked_workspace_bytes(batch); }
 
 // known[c] >= 0: size of bin c (read back by the synchronous driver); < 0: unknown (asynchronous expert
@@ -244,11 +244,11 @@ static magma_int_t vbatched_run(magma_int_t *m, magma_int_t *n, int max_m, int m
         return lu_small_launch(d, max_m, max_n, dA_array, ipiv_array, info_array, 0, nullptr, 0, batch, nullptr, s);
 
     int *lists = (int *)work;
-    int *counts = lists + 5 * batch;
+    int *counts = lists + 7 * batch;
     void *recs = (char *)work + vbatched_lists_bytes(batch);
-    long cnt[5];
-    for (int c = 0; c < 5; ++c) cnt[c] = known ? known[c] : batch;
-    if (!known) cudaMemsetAsync(lists, 0xFF, sizeof(int) * 5 * (size_t)batch, s);
+    long cnt[7];
+    for (int c = 0; c < 7; ++c) cnt[c] = known ? known[c] : batch;
+    if (!known) cudaMemsetAsync(lists, 0xFF, sizeof(int) * 7 * (size_t)batch, s);
     const int mid_max = (g_tier == 2) ? 32 : g_mid_max;
     vbatched_partition_launch(m, n, batch, lists, counts, mid_max, s);
     magma_int_t rc = 0;
@@ -261,8 +261,12 @@ static magma_int_t vbatched_run(magma_int_t *m, magma_int_t *n, int max_m, int m
         if (cnt[c] > 0)
             rc = lu_mid_launch(d, imin(max_m, cap[c - 1]), imin(max_n, cap[c - 1]), dA_array, ipiv_array, info_array,
                                cnt[c], lists + (size_t)c * batch, s);
-    if (rc == 0 && cnt[4] > 0)
-        rc = lu_blocked_launch(d, max_m, max_n, dA_array, ipiv_array, info_array, cnt[4], lists + 4 * (size_t)batch, recs, s);
+    // blocked tier, one step sequence per size class (the pivot records are reused: the stream serialises them)
+    static const int bcap[3] = {256, 384, 0x7fffffff};
+    for (int c = 4; c <= 6 && rc == 0; ++c)
+        if (cnt[c] > 0)
+            rc = lu_blocked_launch(d, imin(max_m, bcap[c - 4]), imin(max_n, bcap[c - 4]), dA_array, ipiv_array, info_array,
+                                   cnt[c], lists + (size_t)c * batch, recs, s);
     return rc;
 }
 
@@ -335,11 +339,12 @@ magma_int_t magma_dgetrf_vbatched(magma_int_t *m, magma_int_t *n, double **dA_ar
     }
     // bin sizes as the partition kernel will produce them (classes above mid_max fall into the last bin)
     const int mid_max = (g_tier == 2) ? 32 : g_mid_max;
-    int known[5] = {h[5], h[8], h[9], h[10], 0};
-    if (mid_max < 64) known[1] = 0;
-    if (mid_max < 96) known[2] = 0;
-    if (mid_max < 128) known[3] = 0;
-    known[4] = h[6] - known[0] - known[1] - known[2] - known[3];
+    int known[7] = {h[5], h[8], h[9], h[10], h[11], h[12], 0};
+    // classes above mid_max belong to the blocked bins (all three are <= 256, so they join bin 4)
+    if (mid_max < 64) { known[4] += known[1]; known[1] = 0; }
+    if (mid_max < 96) { known[4] += known[2]; known[2] = 0; }
+    if (mid_max < 128) { known[4] += known[3]; known[3] = 0; }
+    known[6] = h[6] - known[0] - known[1] - known[2] - known[3] - known[4] - known[5];
     magma_int_t rc = vbatched_run(m, n, max_m, max_n, dA_array, ldda, ipiv_array, info_array, work, batchCount, queue,
                                   known);
     // the reference's driver returns after a queue sync (src/zgetrf_vbatched.cpp:392)

@@ -34,7 +34,8 @@ __global__ void memset_int_kernel(int *p, int v, long n)
 __global__ void vbatched_stats_kernel(const int *__restrict__ m, const int *__restrict__ n,
                                       const int *__restrict__ ldda, long batch, int *out8)
 {
-    int mm = 0, mn_ = 0, mmin = 0, mxn = 0, bad = 0x7fffffff, small = 0, nonempty = 0, c64 = 0, c96 = 0, c128 = 0;
+    int mm = 0, mn_ = 0, mmin = 0, mxn = 0, bad = 0x7fffffff, small = 0, nonempty = 0, c64 = 0, c96 = 0, c128 = 0,
+        c256 = 0, c384 = 0;
     for (long b = (long)blockIdx.x * blockDim.x + threadIdx.x; b < batch; b += (long)gridDim.x * blockDim.x) {
         const int M = m[b], N = n[b], L = ldda[b];
         if (M < 0) bad = min(bad, 1);
@@ -52,6 +53,8 @@ __global__ void vbatched_stats_kernel(const int *__restrict__ m, const int *__re
             else if (K <= 64) ++c64;
             else if (K <= 96) ++c96;
             else if (K <= 128) ++c128;
+            else if (K <= 256) ++c256;
+            else if (K <= 384) ++c384;
         }
     }
     const unsigned full = 0xffffffffu;
@@ -65,6 +68,8 @@ __global__ void vbatched_stats_kernel(const int *__restrict__ m, const int *__re
     c64 = __reduce_add_sync(full, c64);
     c96 = __reduce_add_sync(full, c96);
     c128 = __reduce_add_sync(full, c128);
+    c256 = __reduce_add_sync(full, c256);
+    c384 = __reduce_add_sync(full, c384);
     if ((threadIdx.x & 31) == 0) {
         atomicMax(out8 + 0, mm);
         atomicMax(out8 + 1, mn_);
@@ -76,12 +81,15 @@ __global__ void vbatched_stats_kernel(const int *__restrict__ m, const int *__re
         atomicAdd(out8 + 8, c64);
         atomicAdd(out8 + 9, c96);
         atomicAdd(out8 + 10, c128);
+        atomicAdd(out8 + 11, c256);
+        atomicAdd(out8 + 12, c384);
     }
 }
 
 // Index lists by size class of max(m, n): 0: <= 32 (register tier), 1: <= 64, 2: <= 96, 3: <= mid_max
-// (register-file tier, one list per kernel shape), 4: the rest (blocked tier). List c lives at
-// lists + c * batch. Order inside a list is arbitrary (atomic cursor); empty matrices are dropped.
+// (register-file tier, one list per kernel shape), 4: <= 256, 5: <= 384, 6: the rest (blocked tier: each
+// class runs its own step sequence sized for its own maximum, so a 130 x 130 matrix does not sit in
+// launches sized for 512 x 512). List c lives at lists + c * batch. Order inside a list is arbitrary (atomic cursor); empty matrices are dropped.
 __global__ void vbatched_partition_kernel(const int *__restrict__ m, const int *__restrict__ n, long batch,
                                           int *lists, int *counts, int mid_max)
 {
@@ -91,14 +99,14 @@ __global__ void vbatched_partition_kernel(const int *__restrict__ m, const int *
         const int M = m[b], N = n[b];
         if (M > 0 && N > 0) {
             const int K = max(M, N);
-            cls = K <= 32 ? 0 : (K > mid_max ? 4 : (K <= 64 ? 1 : (K <= 96 ? 2 : 3)));
+            cls = K <= 32 ? 0 : (K > mid_max ? (K <= 256 ? 4 : (K <= 384 ? 5 : 6)) : (K <= 64 ? 1 : (K <= 96 ? 2 : 3)));
         }
     }
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int c = 0; c < 5; ++c) {
+    for (int c = 0; c < 7; ++c) {
         const unsigned bal = __ballot_sync(full, cls == c);
         int base = 0;
         if (lane == 0 && bal) base = atomicAdd(counts + c, __popc(bal));

@@ -121,7 +121,7 @@ void memset_int_launch(int *p, int v, long n, cudaStream_t s);
 // count(max(m,n) <= 32), count_nonempty, 0, count(<= 64), count(<= 96), count(<= 128), ...}
 void vbatched_stats_launch(const int *m, const int *n, const int *ldda, long batch, int *out16,
                            cudaStream_t s);
-// builds five index lists by size class (<= 32, <= 64, <= 96, <= mid_max, rest), list c at lists + c*batch
+// builds seven index lists by size class (<= 32, <= 64, <= 96, <= mid_max, <= 256, <= 384, rest), list c at lists + c*batch
 void vbatched_partition_launch(const int *m, const int *n, long batch, int *lists, int *counts,
                                int mid_max, cudaStream_t s);
 void dlarnv_launch(uint64_t seed48, int64_t n, double *dx, cudaStream_t s);

@@ -398,6 +398,82 @@ def test_full_size_properties(gpu_queue, n, batch):
     assert np.array_equal(db.ipiv[idx].cpu().numpy(), ipr)
 
 
+def _lu_backward_error_on_device(A0, LU, ipiv, n):
+    """max_b ||P A - L U||_F / (n ||A||_F) computed with torch on the device (storage [b, j, i] = A_b(i, j))."""
+    import torch
+    A = A0.transpose(1, 2).clone()                      # [b, i, j]
+    F = LU.transpose(1, 2)
+    L = torch.tril(F, -1) + torch.eye(n, dtype=F.dtype, device=F.device)
+    U = torch.triu(F)
+    idx = torch.arange(A.shape[0], device=A.device)
+    for k in range(n):                                   # LAPACK's forward interchanges
+        p = (ipiv[:, k] - 1).long()
+        rk = A[idx, k, :].clone()
+        A[idx, k, :] = A[idx, p, :]
+        A[idx, p, :] = rk
+    num = torch.linalg.matrix_norm(A - L @ U)
+    den = torch.linalg.matrix_norm(A0.transpose(1, 2)) * n
+    return float((num / den).max())
+
+
+@pytest.mark.parametrize("n,batch,nrhs", [(128, 20000, 0), (512, 600, 16)])
+def test_full_size_properties_mid_and_blocked(gpu_queue, n, batch, nrhs):
+    """BASELINE configs 3 and 5 at (near) full size: the testers' backward-error check on EVERY matrix,
+    computed on the device, pivots in LAPACK range, info == 0, solve residual for config 5, and a
+    bit-exact sample against the oracle."""
+    import torch
+    db = mb.DeviceBatch(batch, n, n, nrhs=nrhs, queue=gpu_queue)
+    seed = np.array([0, 0, 0, 1], dtype=np.int32)
+    mb.dlarnv_uniform(seed, batch * n * n, db.A, gpu_queue)
+    if nrhs:
+        mb.dlarnv_uniform(seed, batch * n * nrhs, db.B, gpu_queue)
+    gpu_queue.sync()
+    A0 = db.A.clone()
+    B0 = db.B.clone() if nrhs else None
+    assert db.getrf() == 0
+    if nrhs:
+        assert db.getrs() == 0
+    gpu_queue.sync()
+    torch.cuda.synchronize()
+    assert int(db.info.abs().max()) == 0
+    lo = torch.arange(1, n + 1, device=db.ipiv.device, dtype=torch.int32)
+    assert bool((db.ipiv >= lo).all()) and bool((db.ipiv <= n).all())
+    err = _lu_backward_error_on_device(A0, db.A, db.ipiv, n)
+    assert err < oracle.TOL, f"backward error {err / oracle.EPS:.2f} eps"
+    if nrhs:
+        Am = A0.transpose(1, 2)
+        X = db.B.transpose(1, 2)
+        R = B0.transpose(1, 2) - Am @ X
+        res = R.abs().sum(dim=1).amax(dim=1) / (n * Am.abs().sum(dim=2).amax(dim=1) * X.abs().sum(dim=1).amax(dim=1))
+        assert float(res.max()) < oracle.TOL
+    idx = np.linspace(0, batch - 1, 6).astype(np.int64)
+    As = A0[idx].cpu().numpy()
+    ipr, _ = oracle.getrf_batched(As, n)
+    assert np.array_equal(db.A[idx].cpu().numpy(), As)
+    assert np.array_equal(db.ipiv[idx].cpu().numpy(), ipr)
+    if nrhs:
+        Bs = B0[idx].cpu().numpy()
+        oracle.getrs_batched(mb.MagmaNoTrans, As, ipr, Bs, n)
+        assert np.array_equal(db.B[idx].cpu().numpy(), Bs)
+
+
+@pytest.mark.parametrize("n,nrhs", [(33, 1), (40, 17), (100, 16), (129, 3), (250, 20), (256, 16), (257, 5), (511, 9)])
+def test_getrs_tensor_pipe_shapes(gpu_queue, n, nrhs):
+    """getrs_dmma_kernel: sizes that are not multiples of 8 / 32, right-hand-side counts around the 16-wide tile."""
+    batch = 5
+    A0, seed = oracle.random_batch(batch, n, n)
+    B0, _ = oracle.random_batch(batch, n, nrhs, iseed=seed)
+    db = mb.DeviceBatch(batch, n, n, nrhs=nrhs, queue=gpu_queue)
+    db.upload(A0, B0)
+    assert db.getrf() == 0
+    assert db.getrs() == 0
+    LU, ipiv, info, X = db.download()
+    Xr = B0.copy()
+    oracle.getrs_batched(mb.MagmaNoTrans, LU, ipiv, Xr, n)
+    assert np.array_equal(X, Xr), f"max diff {np.max(np.abs(X - Xr))}"
+    assert oracle.solve_residual(mb.MagmaNoTrans, A0, X, B0, n) < oracle.TOL
+
+
 def test_host_front_end(gpu_queue):
     """magma_b200_dgesv_batched_host: pageable host buffers in, results out, chunked pipeline."""
     n, batch = 16, 5000

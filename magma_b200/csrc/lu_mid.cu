@@ -81,26 +81,32 @@ __device__ __forceinline__ void st_release_s32(int *p, int v)
 }
 
 // Shared memory of one CTA (dynamic).
-template <int R, int NW>
+template <int R, int NW, int PH>
 struct MidSmem {
-    double Lcol[NW * CW][R * 32];   // multipliers of column j by row slot (0 where the row is not updated)
+    double Lcol[NW * CW][R * 32];   // multipliers of column j (of the current phase) by row slot (0: row not updated)
     double rowbuf[NW][2][CW + 2];   // per warp: pivot row ping-pong, [CW] = 1/pivot
-    int pivslot[NW * CW];           // slot (r*32 + lane) of the pivot row of column j
+    int pivslot[PH * NW * CW];      // slot (r*32 + lane) of the pivot row of column j
     int pos_of[R * 32];             // slot -> current row position
     int slot_at[R * 32];            // row position -> slot
-    int ipiv[NW * CW];
+    int ipiv[PH * NW * CW];
     int colready;                   // columns published so far
     int info;
-    unsigned long long bar[NW * CW];
+    unsigned long long bar[PH * NW * CW];
 };
 
-template <int R, int NW, int MINB>
+// PH = 2: the CTA holds only HALF of the columns in registers at a time. Phase 0 factors column blocks
+// 0..NW-1 and writes them back in their original row order; phase 1 loads blocks NW..2NW-1, catches up on the
+// (already published) columns of phase 0, then factors. At the end the phase-0 columns are re-read and stored
+// at their final row positions. Half the registers per matrix => two matrices per SM at n = 128, i.e. two
+// independent pivot chains to interleave: the chain (~800 cycles per column), not FP64 or HBM, bounds this tier.
+template <int R, int NW, int PH, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB)
 lu_mid_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__restrict__ dinfo, long batch,
               const int *__restrict__ index_list)
 {
+    static_assert(PH == 1 || PH == 2, "phases");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    MidSmem<R, NW> &sm = *reinterpret_cast<MidSmem<R, NW> *>(smem_raw);
+    MidSmem<R, NW, PH> &sm = *reinterpret_cast<MidSmem<R, NW, PH> *>(smem_raw);
 
     const long slotb = blockIdx.x;
     const long b = index_list ? index_list[slotb] : slotb;
@@ -116,44 +122,24 @@ lu_mid_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *_
         sm.info = 0;
         sm.colready = 0;
     }
-    for (int i = tid; i < NW * CW; i += NW * 32) mbar_init((unsigned)__cvta_generic_to_shared(&sm.bar[i]), 1);
+    for (int i = tid; i < PH * NW * CW; i += NW * 32) mbar_init((unsigned)__cvta_generic_to_shared(&sm.bar[i]), 1);
     for (int i = tid; i < R * 32; i += NW * 32) {
         sm.pos_of[i] = i;  // slot r*32 + lane holds row lane + 32 r
         sm.slot_at[i] = i;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    if (w >= nblocks) return;  // no columns here (n <= 8w); nothing below needs this warp
 
     double *__restrict__ A = dA[b];
-    const int c0 = w * CW;
-    const int nc = (n - c0) < CW ? (n - c0) : CW;  // columns of this block
-
     double a[R][CW];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int row = lane + 32 * r;
-#pragma unroll
-        for (int c = 0; c < CW; ++c) a[r][c] = (row < m && c < nc) ? A[row + (size_t)(c0 + c) * ld] : 0.0;
-    }
 
-    // ---- columns to the left: apply each one as soon as it is published -----------------------------
-    const int jend = c0 < mn ? c0 : mn;
-    int ready = 0;
-#pragma unroll 1
-    for (int j = 0; j < jend; ++j) {
-        if (j >= ready) {
-            ready = ld_acquire_s32(&sm.colready);
-            if (j >= ready) {
-                mbar_wait0((unsigned)__cvta_generic_to_shared(&sm.bar[j]));
-                ready = j + 1;
-            }
-        }
+    // one published column applied to this warp's block: U(j, block) from the pivot row's lane, then the update
+    auto apply_column = [&](int j, int lidx) {
         const int s = sm.pivslot[j];
         const int owner = s & 31, rk = s >> 5;
         double l[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) l[r] = sm.Lcol[j][r * 32 + lane];
+        for (int r = 0; r < R; ++r) l[r] = sm.Lcol[lidx][r * 32 + lane];
         double u[CW];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -167,10 +153,46 @@ lu_mid_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *_
 #pragma unroll
             for (int c = 0; c < CW; ++c) a[r][c] = fma(-l[r], u[c], a[r][c]);
         }
+    };
+
+#pragma unroll 1
+  for (int ph = 0; ph < PH; ++ph) {
+    const int pbase = ph * NW * CW;                       // first column of this phase
+    const int c0 = pbase + w * CW;
+    const bool has_block = (ph * NW + w) < nblocks;       // this warp holds columns in this phase
+    const int nc = (n - c0) < CW ? (n - c0) : CW;         // columns of this block
+    if (has_block) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int row = lane + 32 * r;
+#pragma unroll
+            for (int c = 0; c < CW; ++c) a[r][c] = (row < m && c < nc) ? A[row + (size_t)(c0 + c) * ld] : 0.0;
+        }
+    }
+    const int jend = has_block ? (c0 < mn ? c0 : mn) : 0;
+    if (PH > 1 && ph > 0) {
+        // catch up on the previous phase: all of it is published, its multipliers still sit in Lcol
+        const int jc = jend < pbase ? jend : pbase;
+#pragma unroll 1
+        for (int j = 0; j < jc; ++j) apply_column(j, j);
+        __syncthreads();  // every warp is done with the previous phase's Lcol: this phase may overwrite it
+    }
+    // ---- columns of this phase to the left: apply each one as soon as it is published ---------------------
+    int ready = pbase;
+#pragma unroll 1
+    for (int j = pbase; j < jend; ++j) {
+        if (j >= ready) {
+            ready = ld_acquire_s32(&sm.colready);
+            if (j >= ready) {
+                mbar_wait0((unsigned)__cvta_generic_to_shared(&sm.bar[j]));
+                ready = j + 1;
+            }
+        }
+        apply_column(j, j - pbase);
     }
 
     // ---- this warp's own columns ---------------------------------------------------------------------------
-    if (c0 < mn) {
+    if (has_block && c0 < mn) {
         const int jb = (mn - c0) < CW ? (mn - c0) : CW;
         // done: bit r set when row slot (lane, r) has been a pivot row (or does not exist)
         unsigned done = 0;
@@ -278,7 +300,7 @@ lu_mid_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *_
                     const bool upd = nz && !((done >> r) & 1u);
                     l[r] = upd ? a[r][jj] * rr : 0.0;
                     if (upd) a[r][jj] = l[r];
-                    sm.Lcol[j][r * 32 + lane] = l[r];
+                    sm.Lcol[j - pbase][r * 32 + lane] = l[r];
                 }
                 if (info != 0 && lane == 0 && sm.info == 0) sm.info = info;  // columns finish in order
                 __syncwarp();
@@ -295,16 +317,51 @@ lu_mid_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *_
         }
     }
 
+    if (PH > 1 && ph + 1 < PH) {
+        // end of a non-final phase: wait until its last column is out (the catch-up of the next phase does not
+        // wait), then park this block in global memory in its ORIGINAL row order (slot order, coalesced)
+        const int pend = mn < pbase + NW * CW ? mn : pbase + NW * CW;
+        if (pend > pbase) mbar_wait0((unsigned)__cvta_generic_to_shared(&sm.bar[pend - 1]));
+        if (has_block) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int row = lane + 32 * r;
+#pragma unroll
+                for (int c = 0; c < CW; ++c)
+                    if (row < m && c < nc) A[row + (size_t)(c0 + c) * ld] = a[r][c];
+            }
+        }
+    }
+  }  // phases
+
     // ---- final row positions: known once the last column is done -------------------------------------------
     if (mn > 0) mbar_wait0((unsigned)__cvta_generic_to_shared(&sm.bar[mn - 1]));
+    int q[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int row = lane + 32 * r;
-        if (row < m) {
-            const int q = sm.pos_of[r * 32 + lane];
+    for (int r = 0; r < R; ++r) q[r] = sm.pos_of[r * 32 + lane];
+#pragma unroll 1
+    for (int ph = PH - 1; ph >= 0; --ph) {
+        const int c0 = (ph * NW + w) * CW;
+        if ((ph * NW + w) >= nblocks) continue;
+        const int nc = (n - c0) < CW ? (n - c0) : CW;
+        if (ph < PH - 1) {
+            // parked block: read it back (same thread wrote these addresses), all rows before any store
 #pragma unroll
-            for (int c = 0; c < CW; ++c)
-                if (c < nc) A[q + (size_t)(c0 + c) * ld] = a[r][c];
+            for (int r = 0; r < R; ++r) {
+                const int row = lane + 32 * r;
+#pragma unroll
+                for (int c = 0; c < CW; ++c) a[r][c] = (row < m && c < nc) ? A[row + (size_t)(c0 + c) * ld] : 0.0;
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int row = lane + 32 * r;
+            if (row < m) {
+#pragma unroll
+                for (int c = 0; c < CW; ++c)
+                    if (c < nc) A[q[r] + (size_t)(c0 + c) * ld] = a[r][c];
+            }
         }
     }
     if (w == 0) {
@@ -314,11 +371,11 @@ lu_mid_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *_
     }
 }
 
-template <int R, int NW, int MINB>
+template <int R, int NW, int PH, int MINB>
 magma_int_t launch_mid(const Dims &d, double **dA, int **dipiv, int *dinfo, long batch, const int *il, cudaStream_t s)
 {
-    auto k = lu_mid_kernel<R, NW, MINB>;
-    const size_t smem = sizeof(MidSmem<R, NW>);
+    auto k = lu_mid_kernel<R, NW, PH, MINB>;
+    const size_t smem = sizeof(MidSmem<R, NW, PH>);
     static bool once = false;
     if (!once) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -333,14 +390,22 @@ magma_int_t launch_mid(const Dims &d, double **dA, int **dipiv, int *dinfo, long
 }  // namespace
 
 // Register-file-resident LU for max_m <= 128, max_n <= 128. Returns -100 when not covered.
+// R (rows per lane) from the row count, phases from the column count; 8 warps per CTA throughout.
 magma_int_t lu_mid_launch(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo, long batch,
                           const int *index_list, cudaStream_t s)
 {
     if (batch <= 0) return 0;
     if (max_m > 128 || max_n > 128) return -100;
-    if (max_m <= 64 && max_n <= 64) return launch_mid<2, 8, 3>(d, dA, dipiv, dinfo, batch, index_list, s);
-    if (max_m <= 96 && max_n <= 96) return launch_mid<3, 12, 1>(d, dA, dipiv, dinfo, batch, index_list, s);
-    return launch_mid<4, 16, 1>(d, dA, dipiv, dinfo, batch, index_list, s);
+    if (g_small_rows == 8) {  // the single-phase 16-warp kernel (A/B runs)
+        if (max_m <= 64 && max_n <= 64) return launch_mid<2, 8, 1, 3>(d, dA, dipiv, dinfo, batch, index_list, s);
+        return launch_mid<4, 16, 1, 1>(d, dA, dipiv, dinfo, batch, index_list, s);
+    }
+    if (max_m <= 64) {
+        if (max_n <= 64) return launch_mid<2, 8, 1, 3>(d, dA, dipiv, dinfo, batch, index_list, s);
+        return launch_mid<2, 8, 2, 3>(d, dA, dipiv, dinfo, batch, index_list, s);
+    }
+    if (max_n <= 64) return launch_mid<4, 8, 1, 2>(d, dA, dipiv, dinfo, batch, index_list, s);
+    return launch_mid<4, 8, 2, 2>(d, dA, dipiv, dinfo, batch, index_list, s);
 }
 
 }  // namespace mb200

@@ -1,4 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-python tools/run_config.py 16 1000000 1 4 | tail -2
-python tools/run_config.py 16 1000000 0 3 | tail -1
-python tools/run_config.py 8 2000000 0 3 | tail -1
+SMALL_ROWS=2 python -m pytest tests -m gpu -x -q -k "small or golden or singular" 2>&1 | tail -2
+for sr in 0 2; do echo "SMALL_ROWS=$sr"; SMALL_ROWS=$sr python tools/run_config.py 32 1000000 0 3 | tail -1; SMALL_ROWS=$sr python tools/run_config.py 32 10000 0 5 | tail -2; done

@@ -104,12 +104,15 @@ magma_int_t magma_dgetrf_batched(magma_int_t m, magma_int_t n, double **dA_array
         else if (m <= g_mid_max && n <= g_mid_max && g_tier != 2)
             rc = lu_mid_launch(d, m, n, dA_array + off, ipiv_array + off, info_array + off, cnt, nullptr, s);
         if (rc == -100) {
-            void *ws = queue_dscratch(queue, lu_blocked_workspace_bytes(cnt));
+            const size_t rec_bytes = (lu_blocked_workspace_bytes(cnt) + 255) & ~(size_t)255;
+            const size_t perm_bytes = lu_blocked_perm_bytes(cnt, m, n);
+            void *ws = queue_dscratch(queue, rec_bytes + perm_bytes);
             if (!ws) {
                 magma_xerbla(__func__, -MAGMA_ERR_DEVICE_ALLOC);
                 return MAGMA_ERR_DEVICE_ALLOC;
             }
-            rc = lu_blocked_launch(d, m, n, dA_array + off, ipiv_array + off, info_array + off, cnt, nullptr, ws, s);
+            rc = lu_blocked_launch(d, m, n, dA_array + off, ipiv_array + off, info_array + off, cnt, nullptr, ws, s,
+                                   perm_bytes ? (char *)ws + rec_bytes : nullptr);
         }
         if (rc != 0) {
             magma_xerbla(__func__, -rc);
@@ -222,7 +225,18 @@ magma_int_t magma_dgesv_batched(magma_int_t n, magma_int_t nrhs, double **dA_arr
 // tier's pivot records. Matrices are binned by max(m, n) and every bin runs the tier built for it.
 // ---------------------------------------------------------------------------------------------
 static size_t vbatched_lists_bytes(long batch) { return (((size_t)(7 * batch + 8) * sizeof(int)) + 511) & ~(size_t)511; }
-static size_t vbatched_work_bytes(long batch) { return vbatched_lists_bytes(batch) + lu_blocked_workspace_bytes(batch); }
+// lists, pivot records, and (when the total still fits the int-sized lwork of the reference API) the
+// step-permutation records that let the <= 256 class run the left-looking driver
+static size_t vbatched_base_bytes(long batch)
+{
+    return (vbatched_lists_bytes(batch) + lu_blocked_workspace_bytes(batch) + 255) & ~(size_t)255;
+}
+static size_t vbatched_perm_bytes(long batch)
+{
+    const size_t p = lu_blocked_perm_bytes(batch, 256, 256);
+    return (vbatched_base_bytes(batch) + p <= 0x7fffff00ull) ? p : 0;
+}
+static size_t vbatched_work_bytes(long batch) { return vbatched_base_bytes(batch) + vbatched_perm_bytes(batch); }
 
 // known[c] >= 0: size of bin c (read back by the synchronous driver); < 0: unknown (asynchronous expert
 // entries: every list is pre-filled with -1 and launched over `batch` slots, CTAs that draw -1 exit).
@@ -263,10 +277,11 @@ static magma_int_t vbatched_run(magma_int_t *m, magma_int_t *n, int max_m, int m
                                cnt[c], lists + (size_t)c * batch, s);
     // blocked tier, one step sequence per size class (the pivot records are reused: the stream serialises them)
     static const int bcap[3] = {256, 384, 0x7fffffff};
+    void *perm = vbatched_perm_bytes(batch) ? (char *)work + vbatched_base_bytes(batch) : nullptr;
     for (int c = 4; c <= 6 && rc == 0; ++c)
         if (cnt[c] > 0)
             rc = lu_blocked_launch(d, imin(max_m, bcap[c - 4]), imin(max_n, bcap[c - 4]), dA_array, ipiv_array, info_array,
-                                   cnt[c], lists + (size_t)c * batch, recs, s);
+                                   cnt[c], lists + (size_t)c * batch, recs, s, c == 4 ? perm : nullptr);
     return rc;
 }
 

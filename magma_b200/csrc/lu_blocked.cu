@@ -41,8 +41,11 @@ static_assert(sizeof(PivRec) == 512, "PivRec layout");
 template <int R, int W>
 __global__ void __launch_bounds__(512)
 panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__restrict__ dinfo,
-             PivRec *__restrict__ recs, int j, long batch, const int *__restrict__ index_list)
+             PivRec *__restrict__ recs, int j, long batch, const int *__restrict__ index_list,
+             unsigned short *__restrict__ sinv = nullptr, int sinv_rows = 0, int sinv_blocks = 0)
 {
+    // sinv (left-looking driver): sinv[panel][p] = position BEFORE this panel of the row that is at position p
+    // after it (absolute rows, entries >= j only)
     __shared__ unsigned long long cbits[2][32];
     __shared__ int cpos[2][32];
     __shared__ __align__(16) double prow[2][W + 2];  // [W] = 1/pivot
@@ -161,6 +164,8 @@ panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__
             for (int c = 0; c < W; ++c)
                 if (c < jb) A[pos[k] + (size_t)c * ld] = a[k][c];
             const int orig = tid + k * T;
+            if (sinv)
+                sinv[((size_t)slot * sinv_blocks + (j >> 5)) * sinv_rows + j + pos[k]] = (unsigned short)(j + orig);
             if (pos[k] < jb) {
                 rec.top_src[pos[k]] = orig;
             } else if (pos[k] != orig) {  // an original top row that went down
@@ -1019,6 +1024,296 @@ laswp_left_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, in
     }
 }
 
+// -------------------------------------------------------------------------------------------
+// Left-looking column-slab update (matrices of at most 512 rows). One CTA owns the 32-column slab
+// J of one matrix for the whole of its history: it reads the slab ONCE, through the composed row
+// permutation of every earlier panel, keeps it in DMMA accumulator fragments, and for each earlier
+// panel K (increasing) solves the 32 x 32 block row against L_KK and subtracts L(:, K) * U(K, J)
+// from every row below -- the canonical k-increasing order per element, so the result is
+// bit-identical to the right-looking flow. The slab goes back once, rows in current order, ready
+// for its own panel factorisation.
+// Why: the right-looking flow re-reads and re-writes the whole trailing matrix at every step and
+// moves pivot rows with 8-byte scattered accesses (32-byte sectors, read-modify-write): 120 GB of
+// HBM traffic at n = 512 x 4000 against 16.8 GB of matrix, i.e. the FP64 pipe waits on HBM. Here a
+// slab costs one read + one write + one read of the L columns to its left (gathered by row, but the
+// permutation is the identity except for <= 32 rows per panel): ~45 GB in total.
+// L blocks stay in the row order of their own panel (the interchanges of later panels are applied
+// to them in one pass at the end, laswp_left_kernel); rmap[K][i] walks row i back to that order
+// through the per-panel step permutations the panel kernel records (sinv).
+// Warp w owns the 8-row tiles w, w + NW, w + 2NW, w + 3NW (cyclic: the shrinking active region stays
+// balanced); lane (g = lane/4, q = lane%4) holds C(8t+g, 8c+2q) and C(8t+g, 8c+2q+1).
+// -------------------------------------------------------------------------------------------
+constexpr int LL_LDU = 36;  // Us[k*LL_LDU + c]: B fragments (k = 4s+q, c = 8ct+g) hit 32 distinct banks
+constexpr int LL_LDA = 36;  // ring chunk: As[kk*LL_LDA + 8a+g], same property for the A fragments
+constexpr int LL_CHUNK = 8 * LL_LDA;  // doubles per chunk: 8 k-columns x (4 tiles x 8 rows + pad)
+
+template <int NW>
+struct LeftSmem {
+    static constexpr int RING = (NW == 16) ? 4 : 3;  // chunks per warp (RING - 1 in flight)
+    double Us[32 * LL_LDU];                 // block row K of the slab as the owners left it
+    double Un[2][32 * LL_LDU];              // -U(K, J), double buffered (the update of step K reads it while
+                                            // the solve of step K+1 writes the other one)
+    double Ls[2][32 * 33];                  // L_KK, prefetched one step ahead
+    unsigned short rmap[NW][NW * 32];       // row i of the current order -> row in the order of panel K
+    unsigned short src[NW * 32];            // row i of the current order -> original row (slab load)
+    double ring[NW * RING * LL_CHUNK];      // per-warp private L chunks (cp.async); the staged step
+                                            // permutations (NW x NW*32 shorts) live here during set-up
+};
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 16 ? 1 : 2)
+left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__restrict__ sinv_g, int sinv_rows,
+                   int sinv_blocks, int J, int finish, long batch, const int *__restrict__ index_list)
+{
+    // finish = 1: second visit of the slab that holds the LAST, narrower panel of a wide matrix
+    // (32J < min(m,n) < min(n, 32J+32)): its columns right of the panel still need that panel's step.
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LeftSmem<NW> &S = *reinterpret_cast<LeftSmem<NW> *>(smem_raw);
+    constexpr int T = NW * 32;
+    constexpr int RING = LeftSmem<NW>::RING;
+    static_assert(sizeof(unsigned short) * NW * T <= sizeof(double) * NW * RING * LL_CHUNK, "sinv overlay");
+    const unsigned FULLM = 0xffffffffu;
+
+    const long slot = blockIdx.x;
+    const long b = index_list ? index_list[slot] : slot;
+    if (b < 0) return;
+    int m, n, ld;
+    dims_of(d, b, m, n, ld);
+    const int mn = m < n ? m : n;
+    const int c0 = 32 * J;
+    if (c0 >= n) return;
+    const int nc = (n - c0) < 32 ? (n - c0) : 32;
+    if (finish && !(c0 < mn && mn < c0 + nc)) return;
+    const int cb = finish ? mn - c0 : 0;                  // first column of the slab handled here
+    const int kend = finish ? mn : (c0 < mn ? c0 : mn);   // pivots taken so far = rows of the slab that become U
+    const int nk = (kend + 31) >> 5;                      // panels to the left ...
+    const int kfirst = finish ? J : 0;                    // ... of which [kfirst, nk) are still to be applied
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int w = __shfl_sync(FULLM, tid >> 5, 0);
+    const int g = lane >> 2, q = lane & 3;
+    double *__restrict__ A = dA[b];
+
+    // ---- row maps ----------------------------------------------------------------------------------------
+    unsigned short(*sinv_s)[T] = reinterpret_cast<unsigned short(*)[T]>(S.ring);
+    {
+        const unsigned short *sg = sinv_g + (size_t)slot * sinv_blocks * sinv_rows;
+        for (int K = kfirst; K < nk; ++K) sinv_s[K][tid] = (tid < m) ? sg[(size_t)K * sinv_rows + tid] : (unsigned short)tid;
+    }
+    __syncthreads();
+    {
+        int r = tid;
+        for (int K = nk - 1; K >= kfirst; --K) {
+            S.rmap[K][tid] = (unsigned short)r;
+            if (r >= 32 * K) r = sinv_s[K][r];
+        }
+        S.src[tid] = (unsigned short)r;
+    }
+    __syncthreads();  // maps complete; the ring may be overwritten
+
+    // ---- L chunk pipeline: chunk 4K+ch = columns 32K+8ch .. +8 of L, this warp's rows, gathered by rmap[K].
+    // Every lane copies exactly the elements its own A fragments will read (row 8a+g, k 4s+q): no cross-lane
+    // hand-off, cp.async.wait_group is the only synchronisation.
+    double *myring = S.ring + (size_t)w * RING * LL_CHUNK;
+    const unsigned ring_lane = (unsigned)__cvta_generic_to_shared(myring + q * LL_LDA + g);  // + slot, kk, tile offsets
+    int roff[4];      // row of L (order of panel issue_K) behind each of this lane's four tile rows
+    int issue_K = -1;
+    auto issue = [&](int nchunk, int slot_in_ring) {
+        const int K = nchunk >> 2, ch = nchunk & 3;
+        if (K >= nk) return;
+        if (K != issue_K) {
+            issue_K = K;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int row = 8 * (w + NW * a) + g;
+                roff[a] = (row < m) ? (int)S.rmap[K][row] : 0;  // rows past m: any valid address, never stored
+            }
+        }
+        const int kbK = (kend - 32 * K) < 32 ? (kend - 32 * K) : 32;
+        const unsigned dst = ring_lane + (unsigned)(slot_in_ring * LL_CHUNK * 8);
+        const double *col0 = A + (size_t)(32 * K + 8 * ch + q) * ld;
+        if (kbK == 32) {
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const double *colp = col0 + (size_t)(4 * s2) * ld;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int t = w + NW * a;
+                    if (t > 4 * K + 3 && 8 * t < m)  // warp-uniform: the tile lies below block row K
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)((4 * s2 * LL_LDA + 8 * a) * 8)),
+                                     "l"(colp + roff[a])
+                                     : "memory");
+                }
+            }
+        } else {  // last, narrower panel of a wide matrix: zero-fill the missing k
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const bool kok = (8 * ch + 4 * s2 + q) < kbK;
+                const double *colp = kok ? col0 + (size_t)(4 * s2) * ld : A;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int t = w + NW * a;
+                    if (t > 4 * K + 3 && 8 * t < m) {
+                        const int sz = kok ? 8 : 0;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + (unsigned)((4 * s2 * LL_LDA + 8 * a) * 8)),
+                                     "l"(colp + (kok ? roff[a] : 0)), "r"(sz)
+                                     : "memory");
+                    }
+                }
+            }
+        }
+    };
+    auto stage_lkk = [&](int K) {  // L_KK -> Ls[K & 1], zero outside the panel width
+        const int kbK = (kend - 32 * K) < 32 ? (kend - 32 * K) : 32;
+        const double *LKK = A + (size_t)(32 * K) + (size_t)(32 * K) * ld;
+        for (int idx = tid; idx < 1024; idx += T) {
+            const int i = idx & 31, k = idx >> 5;
+            const bool ok = (i < kbK && k < kbK);
+            cp_async8(&S.Ls[K & 1][i * 33 + k], ok ? LKK + i + (size_t)k * ld : A, ok);
+        }
+    };
+    stage_lkk(kfirst);
+#pragma unroll
+    for (int pch = 0; pch < RING - 1; ++pch) {
+        issue(4 * kfirst + pch, pch);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    // ---- the slab, rows in current order ---------------------------------------------------------------------
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int row = 8 * (w + NW * a) + g;
+        const bool rok = row < m;
+        const double *src = A + S.src[row] + (size_t)(c0 + 2 * q) * ld;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int col = 8 * c + 2 * q;
+            acc[a][c][0] = (rok && col >= cb && col < nc) ? src[(size_t)(8 * c) * ld] : 0.0;
+            acc[a][c][1] = (rok && col + 1 >= cb && col + 1 < nc) ? src[(size_t)(8 * c + 1) * ld] : 0.0;
+        }
+    }
+    asm volatile("cp.async.wait_group %0;" ::"n"(RING - 2) : "memory");  // first group: L_KK of the first step
+    __syncthreads();  // every row is in registers: stores into the slab may begin
+
+    int rslot = 0;  // ring slot of the chunk consumed next
+#pragma unroll 1
+    for (int K = kfirst; K < nk; ++K) {
+        const int kb = (kend - 32 * K) < 32 ? (kend - 32 * K) : 32;
+        // ---- block row K -> Us -----------------------------------------------------------------------------
+        {
+            const int aK = (4 * K) / NW;            // accumulator slot of the block row's tiles
+            const int tt = w - (4 * K) % NW;        // which of its four tiles this warp holds, if any
+            if (tt >= 0 && tt < 4) {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    if (a == aK) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            *reinterpret_cast<double2 *>(&S.Us[(8 * tt + g) * LL_LDU + 8 * c + 2 * q]) =
+                                make_double2(acc[a][c][0], acc[a][c][1]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- U(K, J) = L_KK^-1 * block row: column 4w+q, rows g, g+8, g+16, g+24 per lane ----------------------
+        if (w < 8) {
+            const int cc = 4 * w + q;
+            const double *Lk = S.Ls[K & 1];
+            double x[4];
+#pragma unroll
+            for (int sblk = 0; sblk < 4; ++sblk) x[sblk] = S.Us[(g + 8 * sblk) * LL_LDU + cc];
+#pragma unroll
+            for (int k = 0; k < 31; ++k) {
+                const double u = __shfl_sync(FULLM, x[k >> 3], ((k & 7) << 2) | q);
+#pragma unroll
+                for (int sblk = 0; sblk < 4; ++sblk) {
+                    if (8 * sblk + 7 > k) {  // static: this row group still has rows below k
+                        const int i = g + 8 * sblk;
+                        const double l = Lk[i * 33 + k];
+                        if (i > k) x[sblk] = fma(-l, u, x[sblk]);
+                    }
+                }
+            }
+            const bool cok = (cc >= cb && cc < nc);
+            double *Un = S.Un[K & 1];
+#pragma unroll
+            for (int sblk = 0; sblk < 4; ++sblk) {
+                const int i = g + 8 * sblk;
+                Un[i * LL_LDU + cc] = -x[sblk];
+                if (cok && i < kb) A[(size_t)(32 * K + i) + (size_t)(c0 + cc) * ld] = x[sblk];  // final rows of U
+            }
+        }
+        __syncthreads();
+        // ---- rows below: C -= L(:, K) * U(K, J) on the tensor pipe, L streamed through the ring ---------------
+        bool on[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int t = w + NW * a;
+            on[a] = (t > 4 * K + 3) && (8 * t < m);  // warp-uniform
+        }
+        const double *Un = S.Un[K & 1];
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+            {
+                int islot = rslot + RING - 1;
+                if (islot >= RING) islot -= RING;
+                issue(4 * K + ch + RING - 1, islot);
+                if (ch == 0 && K + 1 < nk) stage_lkk(K + 1);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory");
+            }
+            const double *As = myring + rslot * LL_CHUNK + q * LL_LDA + g;
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                double bf[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) bf[c] = Un[(8 * ch + 4 * s2 + q) * LL_LDU + 8 * c + g];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    if (on[a]) {
+                        const double af = As[4 * s2 * LL_LDA + 8 * a];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) dmma_884(acc[a][c][0], acc[a][c][1], af, bf[c]);
+                    }
+                }
+            }
+            if (++rslot == RING) rslot = 0;
+        }
+    }
+
+    // ---- rows that are not U yet go back, current order ---------------------------------------------------------
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int row = 8 * (w + NW * a) + g;
+        if (row >= kend && row < m) {
+            double *dst = A + row + (size_t)(c0 + 2 * q) * ld;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int col = 8 * c + 2 * q;
+                if (col >= cb && col < nc) dst[(size_t)(8 * c) * ld] = acc[a][c][0];
+                if (col + 1 >= cb && col + 1 < nc) dst[(size_t)(8 * c + 1) * ld] = acc[a][c][1];
+            }
+        }
+    }
+}
+
+template <int NW>
+magma_int_t launch_left_update(const Dims &d, double **dA, const unsigned short *sinv, int sinv_rows, int sinv_blocks,
+                               int J, int finish, long batch, const int *il, cudaStream_t s)
+{
+    const size_t smem = sizeof(LeftSmem<NW>);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(left_update_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    left_update_kernel<NW><<<(unsigned)batch, NW * 32, smem, s>>>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, batch, il);
+    count_launch();
+    MB200_CHECK_LAUNCH("left_update_kernel");
+    return 0;
+}
+
 // C[rs.., cs..climit) -= A[:, k0..k0+KW) * A[k0..k0+KW, :) over at most rows_max x cols_max per matrix
 template <int KW>
 magma_int_t launch_gemm_dmma(const Dims &d, double **dA, int k0, int rs, int cs, int climit, int rows_max, int cols_max,
@@ -1158,12 +1453,74 @@ magma_int_t run_step(const Dims &d, int max_m, int max_n, double **dA, int **dip
 
 size_t lu_blocked_workspace_bytes(long batch) { return sizeof(PivRec) * (size_t)(batch > 0 ? batch : 0); }
 
+// Step-permutation records of the left-looking driver: ceil(min(m,n)/32) arrays of roundup(m,32) 16-bit rows
+// per matrix; 0 when the shape is outside that driver (more than 512 rows, or a single panel).
+size_t lu_blocked_perm_bytes(long batch, int max_m, int max_n)
+{
+    const int mn = max_m < max_n ? max_m : max_n;
+    // more than 256 rows: one CTA per SM (16 warps x 128 registers) cannot overlap its solve / load phases with the
+    // tensor-pipe phase and is not ahead of the right-looking flow yet (profiles/README.md); tier 7 forces it
+    if (batch <= 0 || max_n <= 32 || max_m > 512 || (max_m > 256 && g_tier != 7)) return 0;
+    const size_t rows = (size_t)((max_m + 31) / 32) * 32, blocks = (size_t)(mn + 31) / 32;
+    return sizeof(unsigned short) * rows * blocks * (size_t)batch;
+}
+
+namespace {
+
+// Left-looking driver (max_m <= 512): per 32-column slab one update kernel (everything to its left, once)
+// and one panel kernel; the interchanges of the L columns in one pass at the end.
+magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo, PivRec *recs,
+                             unsigned short *sinv, long batch, const int *il, cudaStream_t s)
+{
+    const int max_mn = max_m < max_n ? max_m : max_n;
+    const int sinv_rows = ((max_m + 31) / 32) * 32, sinv_blocks = (max_mn + 31) / 32;
+    const int slabs = (max_n + 31) / 32;
+    auto left = [&](int J, int finish) -> magma_int_t {
+        return (max_m <= 256) ? launch_left_update<8>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, batch, il, s)
+                              : launch_left_update<16>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, batch, il, s);
+    };
+    for (int J = 0; J < slabs; ++J) {
+        magma_int_t rc = 0;
+        if (J > 0) rc = left(J, 0);
+        if (rc != 0) return rc;
+        const int j = 32 * J;
+        if (j < max_mn) {
+            const int T = ((max_m - j + 31) / 32) * 32;
+            panel_kernel<1, 32><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+            count_launch();
+            MB200_CHECK_LAUNCH("panel_kernel");
+            // a last, narrower panel with columns to its right in the same slab (wide matrices). Variable sizes:
+            // any panel may be some matrix's last one, the kernel sorts that out per matrix.
+            const bool partial_here = d.vm ? (max_n > j + 1) : (max_mn < j + 32 && max_n > max_mn);
+            if (partial_here && (rc = left(J, 1)) != 0) return rc;
+        }
+    }
+    if (max_mn > 32) {
+        const int blocks = (max_mn - 1) / 32;
+        const int max_rows = max_m - 32;
+        const size_t smem = sizeof(int) * 2 * (size_t)max_rows + 16 + sizeof(double) * LSWP_COLS * (size_t)max_rows;
+        const long grid = (long)blocks * batch;
+        if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
+        laswp_left_kernel<<<(unsigned)grid, LSWP_THREADS, smem, s>>>(d, dA, dipiv, blocks, max_rows, 32, 0, batch, il);
+        count_launch();
+        MB200_CHECK_LAUNCH("laswp_left_kernel");
+    }
+    return 0;
+}
+
+}  // namespace
+
 magma_int_t lu_blocked_launch(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo,
-                              long batch, const int *index_list, void *workspace, cudaStream_t s)
+                              long batch, const int *index_list, void *workspace, cudaStream_t s, void *perm_workspace)
 {
     if (batch <= 0) return 0;
     PivRec *recs = reinterpret_cast<PivRec *>(workspace);
     const int max_mn = max_m < max_n ? max_m : max_n;  // upper bound of min(m_b, n_b)
+    // tiers 4 (DFMA only), 5 (no pairing), 6 (right-looking) keep the right-looking flow for A/B runs
+    if (perm_workspace && max_n > 32 && (max_m <= 256 || (max_m <= 512 && g_tier == 7)) && g_tier != 4 && g_tier != 5 &&
+        g_tier != 6)
+        return run_left_looking(d, max_m, max_n, dA, dipiv, dinfo, recs, reinterpret_cast<unsigned short *>(perm_workspace),
+                                batch, index_list, s);
     const bool defer_left = (max_m <= 512);             // every step is 32 wide
     int pair_end_block = 0;                              // column blocks < this were factored in 64-wide pairs
     int j = 0;

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q -k "blocked or rect or getrf" > gpurun_out/r11_tests.log 2>&1; echo "tests rc $?" >> gpurun_out/r11_tests.log
+tail -5 gpurun_out/r11_tests.log
+for n in 512 384 256 160; do
+  b=$((4000*512*512/n/n))
+  timeout 120 python tools/run_config.py $n $b 0 3 | tail -1
+  TIER=6 timeout 120 python tools/run_config.py $n $b 0 3 | tail -1
+done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r11_launches.csv python tools/run_config.py 512 4000 0 1 > /dev/null 2>&1
+python tools/launch_summary.py gpurun_out/r11_launches.csv 2>/dev/null | head -6
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:left_update --launch-skip 7 --launch-count 1 -o gpurun_out/left8b -f python tools/run_config.py 512 592 0 1 > gpurun_out/r11_ncu.log 2>&1

@@ -17,6 +17,7 @@
 //                   CTA (4x8 register tiles, operands staged once in shared memory).
 // All arithmetic is in the canonical order of oracle/lu_oracle.c: bit-identical factors.
 #include "lu_common.cuh"
+#include <type_traits>
 
 namespace mb200 {
 
@@ -1246,39 +1247,56 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
         }
         __syncthreads();
         // ---- rows below: C -= L(:, K) * U(K, J) on the tensor pipe, L streamed through the ring ---------------
-        bool on[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int t = w + NW * a;
-            on[a] = (t > 4 * K + 3) && (8 * t < m);  // warp-uniform
-        }
+        // A warp's tiles leave the active region in order (a = 0 first): the pass is specialised on the number
+        // of tiles already out. (With a per-tile `if` ptxas predicates the DMMAs instead of branching, and a
+        // predicated-off DMMA still occupies the tensor pipe: half of its cycles in the late slabs.)
         const double *Un = S.Un[K & 1];
+        auto ring_pass = [&](auto amin_c) {
+            constexpr int AMIN = decltype(amin_c)::value;
+            bool on[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) on[a] = (a >= AMIN) && (8 * (w + NW * a) < m);  // rows past m: predicated
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-            {
-                int islot = rslot + RING - 1;
-                if (islot >= RING) islot -= RING;
-                issue(4 * K + ch + RING - 1, islot);
-                if (ch == 0 && K + 1 < nk) stage_lkk(K + 1);
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory");
-            }
-            const double *As = myring + rslot * LL_CHUNK + q * LL_LDA + g;
+            for (int ch = 0; ch < 4; ++ch) {
+                {
+                    int islot = rslot + RING - 1;
+                    if (islot >= RING) islot -= RING;
+                    issue(4 * K + ch + RING - 1, islot);
+                    if (ch == 0 && K + 1 < nk) stage_lkk(K + 1);
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory");
+                }
+                if (AMIN < 4) {
+                    const double *As = myring + rslot * LL_CHUNK + q * LL_LDA + g;
 #pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-                double bf[4];
+                    for (int s2 = 0; s2 < 2; ++s2) {
+                        double bf[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) bf[c] = Un[(8 * ch + 4 * s2 + q) * LL_LDU + 8 * c + g];
+                        for (int c = 0; c < 4; ++c) bf[c] = Un[(8 * ch + 4 * s2 + q) * LL_LDU + 8 * c + g];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    if (on[a]) {
-                        const double af = As[4 * s2 * LL_LDA + 8 * a];
+                        for (int a = AMIN; a < 4; ++a) {
+                            if (on[a]) {
+                                const double af = As[4 * s2 * LL_LDA + 8 * a];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) dmma_884(acc[a][c][0], acc[a][c][1], af, bf[c]);
+                                for (int c = 0; c < 4; ++c) dmma_884(acc[a][c][0], acc[a][c][1], af, bf[c]);
+                            }
+                        }
                     }
                 }
+                if (++rslot == RING) rslot = 0;
             }
-            if (++rslot == RING) rslot = 0;
+        };
+        {
+            // first tile slot a with w + NW a > 4K + 3
+            const int need = 4 * K + 4 - w;  // tiles t >= 4K+4  <=>  NW a >= need
+            const int amin = need <= 0 ? 0 : (need + NW - 1) / NW;
+            switch (amin) {
+                case 0: ring_pass(std::integral_constant<int, 0>{}); break;
+                case 1: ring_pass(std::integral_constant<int, 1>{}); break;
+                case 2: ring_pass(std::integral_constant<int, 2>{}); break;
+                case 3: ring_pass(std::integral_constant<int, 3>{}); break;
+                default: ring_pass(std::integral_constant<int, 4>{}); break;
+            }
         }
     }
 
@@ -1458,9 +1476,10 @@ size_t lu_blocked_workspace_bytes(long batch) { return sizeof(PivRec) * (size_t)
 size_t lu_blocked_perm_bytes(long batch, int max_m, int max_n)
 {
     const int mn = max_m < max_n ? max_m : max_n;
-    // more than 256 rows: one CTA per SM (16 warps x 128 registers) cannot overlap its solve / load phases with the
-    // tensor-pipe phase and is not ahead of the right-looking flow yet (profiles/README.md); tier 7 forces it
-    if (batch <= 0 || max_n <= 32 || max_m > 512 || (max_m > 256 && g_tier != 7)) return 0;
+    // more than 384 rows: one CTA per SM (16 warps x 128 registers) cannot overlap its solve / load phases with the
+    // tensor-pipe phase and is level with the right-looking flow (n = 512: 43.7 vs 43.1 ms; n = 384: 37.9 vs 38.8;
+    // profiles/README.md); tier 7 forces it
+    if (batch <= 0 || max_n <= 32 || max_m > 512 || (max_m > 384 && g_tier != 7)) return 0;
     const size_t rows = (size_t)((max_m + 31) / 32) * 32, blocks = (size_t)(mn + 31) / 32;
     return sizeof(unsigned short) * rows * blocks * (size_t)batch;
 }
@@ -1517,7 +1536,7 @@ magma_int_t lu_blocked_launch(const Dims &d, int max_m, int max_n, double **dA, 
     PivRec *recs = reinterpret_cast<PivRec *>(workspace);
     const int max_mn = max_m < max_n ? max_m : max_n;  // upper bound of min(m_b, n_b)
     // tiers 4 (DFMA only), 5 (no pairing), 6 (right-looking) keep the right-looking flow for A/B runs
-    if (perm_workspace && max_n > 32 && (max_m <= 256 || (max_m <= 512 && g_tier == 7)) && g_tier != 4 && g_tier != 5 &&
+    if (perm_workspace && max_n > 32 && (max_m <= 384 || (max_m <= 512 && g_tier == 7)) && g_tier != 4 && g_tier != 5 &&
         g_tier != 6)
         return run_left_looking(d, max_m, max_n, dA, dipiv, dinfo, recs, reinterpret_cast<unsigned short *>(perm_workspace),
                                 batch, index_list, s);

@@ -178,6 +178,45 @@ def test_blocked_tier_on_small_sizes(gpu_queue):
         mb.set_tier(0)
 
 
+@pytest.mark.parametrize("m,n,batch", [(400, 400, 3), (512, 512, 2), (300, 70, 4), (300, 500, 3), (257, 300, 3),
+                                       (500, 90, 3), (390, 33, 3)])
+def test_left_looking_16_warps(gpu_queue, m, n, batch):
+    """Tier 7: the left-looking slab driver with 16 warps per slab (257..512 rows; not the default there)."""
+    mb.set_tier(7)
+    try:
+        A0, _ = oracle.random_batch(batch, m, n)
+        check_against_oracle(gpu_queue, A0, m)
+    finally:
+        mb.set_tier(0)
+
+
+@pytest.mark.parametrize("m,n,batch", [(200, 200, 4), (256, 256, 3), (70, 300, 4), (150, 40, 5)])
+def test_right_looking_forced(gpu_queue, m, n, batch):
+    """Tier 6: the right-looking flow on shapes the left-looking driver takes by default."""
+    mb.set_tier(6)
+    try:
+        A0, _ = oracle.random_batch(batch, m, n)
+        check_against_oracle(gpu_queue, A0, m)
+    finally:
+        mb.set_tier(0)
+
+
+def test_left_looking_singular_and_ties(gpu_queue):
+    """Zero columns, duplicate rows and integer ties through the left-looking driver (n = 160)."""
+    rng = np.random.default_rng(11)
+    n = 160
+    mats = [rng.integers(-2, 3, size=(n, n)).astype(float)]
+    Z = rng.random((n, n))
+    Z[:, 40] = 0.0
+    Z[:, 41] = 0.0
+    mats.append(Z)
+    Z2 = rng.random((n, n))
+    Z2[n // 2:, :] = Z2[:n - n // 2, :]
+    mats.append(Z2)
+    mats.append(np.zeros((n, n)))
+    check_against_oracle(gpu_queue, np.stack(mats), n)
+
+
 # ---- solves -----------------------------------------------------------------------------------
 
 def run_gesv(q, A0, B0, n, ldda=None, lddb=None):

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q -k "blocked or rect or getrf or left or right or vbatched" > gpurun_out/r14_tests.log 2>&1; echo "tests rc $?" >> gpurun_out/r14_tests.log
+tail -4 gpurun_out/r14_tests.log
+for n in 512 384; do
+  b=$((4000*512*512/n/n))
+  TIER=7 timeout 120 python tools/run_config.py $n $b 0 3 | tail -1
+done
+for n in 256 160; do
+  b=$((4000*512*512/n/n))
+  timeout 120 python tools/run_config.py $n $b 0 3 | tail -1
+done

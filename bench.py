@@ -423,6 +423,29 @@ def run_sweep(mb, torch, np, q, local, rank, world, barrier, max_over_ranks, sum
     fixed("C1b dgetrf_batched n=32 batch=1000000", 32, 1_000_000)
     fixed("C3 dgetrf_batched n=128 batch=50000", 128, 50_000)
     fixed("C5 dgetrf_batched n=512 batch=4000 (+dgetrs nrhs=16)", 512, 4_000, nrhs=16, solve_after=True, reps=3)
+    fixed("X1 dgetrf_batched n=256 batch=16000 (left-looking slab driver)", 256, 16_000, reps=3)
+
+    # F1: out-of-place inverse from the factors, n = 64: identity fill + the getrs path.
+    # FLOPs: testing/flops.h:87-88,279 (FLOPS_DGETRI); bytes: read LU, write inv(A).
+    def getri(name, n, batch, reps=5):
+        db = mb.DeviceBatch(batch, n, n, nrhs=n, device=local, queue=q)
+        seed = np.array([31, rank, 0, 1], dtype=np.int32)
+        mb.dlarnv_uniform(seed, batch * n * n, db.A, q)
+        q.sync()
+        assert db.getrf() == 0
+        fn = lambda: mb.magma_dgetri_outofplace_batched(n, db.dA_array, db.ldda, db.dipiv_array, db.dB_array,  # noqa: E731
+                                                        db.lddb, db.info, batch, q)
+        med, best = timed(fn, lambda: None, reps)
+        fl = n * ((5. / 6.) + n * ((2. / 3.) * n + 0.5)) + n * ((5. / 6.) + n * ((2. / 3.) * n - 1.5))
+        gf = fl * batch * world / (med * 1e-3) / 1e9
+        roof = min(fl / (16.0 * n * n) * hbm_peak, fp64_peak)
+        out.append({"config": name, "n": n, "batch_per_gpu": batch, "ms": med, "ms_best": best, "gflops": gf,
+                    "gflops_per_gpu": gf / world, "roofline_gflops": roof, "frac_of_roofline": gf / world / roof,
+                    "alg_GBs_per_gpu": 16.0 * n * n * batch / (med * 1e-3) / 1e9})
+        del db
+        torch.cuda.empty_cache()
+
+    getri("F1 dgetri_outofplace_batched n=64 batch=100000", 64, 100_000)
 
     # C4: vbatched, sizes 16 + (lcg mod 497), square, ldda = n
     batch = 20_000

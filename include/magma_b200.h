@@ -208,6 +208,15 @@ magma_int_t magma_dgesv_batched(magma_int_t n, magma_int_t nrhs, double **dA_arr
                                 magma_int_t **dipiv_array, double **dB_array, magma_int_t lddb,
                                 magma_int_t *dinfo_array, magma_int_t batchCount, magma_queue_t queue);
 
+/* inv(A_b) from the factors of magma_dgetrf_batched, out of place (dA_array is read only here; the reference
+ * documents it as in/out but never writes it).   src/zgetri_outofplace_batched.cpp:81-141,
+ * prototype include/magma_zbatched.h:871-878. errors: -1 n, -3 ldda, -6 lddia. info_array is not written
+ * (as in the reference). Asynchronous on the queue (the reference ends with magma_queue_sync). */
+magma_int_t magma_dgetri_outofplace_batched(magma_int_t n, double **dA_array, magma_int_t ldda,
+                                            magma_int_t **dipiv_array, double **dinvA_array,
+                                            magma_int_t lddia, magma_int_t *info_array,
+                                            magma_int_t batchCount, magma_queue_t queue);
+
 /* Variable sizes; m, n, ldda are DEVICE arrays of length batchCount.
  * src/zgetrf_vbatched.cpp:340-398 (checker + setup + workspace inside, blocks the host). */
 magma_int_t magma_dgetrf_vbatched(magma_int_t *m, magma_int_t *n, double **dA_array, magma_int_t *ldda,

@@ -25,7 +25,7 @@ __all__ = [
     "MagmaNoTrans", "MagmaTrans", "MagmaConjTrans", "MagmaUpper", "MagmaLower", "MagmaNonUnit",
     "MagmaUnit", "MagmaLeft", "MagmaRight", "Queue", "ptr", "magma_init", "magma_finalize",
     "magma_dgetrf_batched", "magma_dgetrs_batched", "magma_dgesv_batched", "magma_dgetrf_vbatched",
-    "magma_dgetrf_vbatched_max_nocheck_work", "magma_dgetrf_batched_smallsq_noshfl",
+    "magma_dgetrf_vbatched_max_nocheck_work", "magma_dgetrf_batched_smallsq_noshfl", "magma_dgetri_outofplace_batched",
     "magma_dgesv_batched_small", "magma_dset_pointer", "magma_iset_pointer", "magma_ddisplace_pointers",
     "magma_dlaswp_rowserial_batched", "magmablas_dtrsm_batched", "magma_dgemm_batched_core",
     "magma_get_dgetrf_batched_nbparam", "dlarnv_uniform", "set_tier", "set_small_rows", "set_mid_max", "launch_count",
@@ -132,6 +132,13 @@ def magma_dgetrf_vbatched_max_nocheck_work(m, n, max_m, max_n, max_minmn, max_mx
 def magma_dgetrf_batched_smallsq_noshfl(n, dA_array, ldda, ipiv_array, info_array, batchCount, queue) -> int:
     return _lib.load().magma_dgetrf_batched_smallsq_noshfl(n, ptr(dA_array), ldda, ptr(ipiv_array),
                                                            ptr(info_array), batchCount, _q(queue))
+
+
+def magma_dgetri_outofplace_batched(n, dA_array, ldda, dipiv_array, dinvA_array, lddia, info_array, batchCount,
+                                    queue) -> int:
+    """inv(A) from the factors, out of place (src/zgetri_outofplace_batched.cpp:81)."""
+    return _lib.load().magma_dgetri_outofplace_batched(n, ptr(dA_array), ldda, ptr(dipiv_array), ptr(dinvA_array),
+                                                       lddia, ptr(info_array), batchCount, _q(queue))
 
 
 def magma_dgesv_batched_small(n, nrhs, dA_array, ldda, dipiv_array, dB_array, lddb, dinfo_array, batchCount,

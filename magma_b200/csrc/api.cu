@@ -197,6 +197,29 @@ magma_int_t magma_dgetrs_batched(magma_trans_t trans, magma_int_t n, magma_int_t
     return 0;
 }
 
+// inv(A_b) from the factors, out of place.   src/zgetri_outofplace_batched.cpp:81-141
+// The reference forms U^-1 L^-1 I and then applies the column interchanges in reverse; column j of that product is
+// U^-1 L^-1 e_pi(j), i.e. exactly the solve A X = I with the interchanges applied to the identity first: one
+// identity fill + the getrs path (same kernels, same canonical order as oracle_dgetrs), nothing is re-derived.
+// Like the reference, info_array is not written and dA_array is left untouched.
+magma_int_t magma_dgetri_outofplace_batched(magma_int_t n, double **dA_array, magma_int_t ldda,
+                                            magma_int_t **dipiv_array, double **dinvA_array, magma_int_t lddia,
+                                            magma_int_t *info_array, magma_int_t batchCount, magma_queue_t queue)
+{
+    (void)info_array;
+    magma_int_t info = 0;
+    if (n < 0) info = -1;
+    else if (ldda < imax(1, n)) info = -3;
+    else if (lddia < imax(1, n)) info = -6;
+    if (info != 0) {
+        magma_xerbla(__func__, -info);
+        return info;
+    }
+    if (n == 0 || batchCount <= 0) return 0;
+    identity_launch(n, dinvA_array, lddia, batchCount, queue->stream);
+    return magma_dgetrs_batched(MagmaNoTrans, n, n, dA_array, ldda, dipiv_array, dinvA_array, lddia, batchCount, queue);
+}
+
 magma_int_t magma_dgesv_batched(magma_int_t n, magma_int_t nrhs, double **dA_array, magma_int_t ldda,
                                 magma_int_t **dipiv_array, double **dB_array, magma_int_t lddb,
                                 magma_int_t *dinfo_array, magma_int_t batchCount, magma_queue_t queue)

@@ -24,6 +24,19 @@ __global__ void displace_pointers_kernel(void **out, void **in, long elem, long 
     if (b < batch) out[b] = (char *)in[b] + elem * (row + col * lda);
 }
 
+// dB_b = I (n x n): the right-hand side of the out-of-place inverse (replaces magmablas_zlaset_batched in
+// src/zgetri_outofplace_batched.cpp:114)
+__global__ void identity_kernel(int n, double **__restrict__ dB, int lddb, long batch)
+{
+    const long b = blockIdx.y;
+    double *__restrict__ B = dB[b];
+    const long total = (long)n * n;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % n), j = (int)(idx / n);
+        B[i + (size_t)j * lddb] = (i == j) ? 1.0 : 0.0;
+    }
+}
+
 __global__ void memset_int_kernel(int *p, int v, long n)
 {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -212,6 +225,19 @@ void displace_pointers_launch(void **out, void **in, long elem, long lda, long r
     displace_pointers_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, s>>>(out, in, elem, lda, row, col, batch);
     count_launch();
     MB200_CHECK_LAUNCH_VOID("displace_pointers_kernel");
+}
+
+void identity_launch(int n, double **dB, int lddb, long batch, cudaStream_t s)
+{
+    if (n <= 0 || batch <= 0) return;
+    const long total = (long)n * n;
+    int gx = (int)((total + 255) / 256);
+    if (gx > 64) gx = 64;
+    for (long off = 0; off < batch; off += 65535) {
+        const long cnt = batch - off < 65535 ? batch - off : 65535;
+        identity_kernel<<<dim3((unsigned)gx, (unsigned)cnt), 256, 0, s>>>(n, dB + off, lddb, cnt);
+        count_launch();
+    }
 }
 
 void memset_int_launch(int *p, int v, long n, cudaStream_t s)

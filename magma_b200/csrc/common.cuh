@@ -119,6 +119,7 @@ void set_pointer_launch(void **out, char *base, long elem, long lda, long row, l
 void displace_pointers_launch(void **out, void **in, long elem, long lda, long row, long col,
                               long batch, cudaStream_t s);
 void memset_int_launch(int *p, int v, long n, cudaStream_t s);
+void identity_launch(int n, double **dB, int lddb, long batch, cudaStream_t s);
 // vbatched statistics: out[0..15] = {max_m, max_n, max_minmn, max_mxn(clamped), first_bad_arg,
 // count(max(m,n) <= 32), count_nonempty, 0, count(<= 64), count(<= 96), count(<= 128), ...}
 void vbatched_stats_launch(const int *m, const int *n, const int *ldda, long batch, int *out16,

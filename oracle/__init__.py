@@ -162,6 +162,17 @@ def gesv_batched(A: np.ndarray, B: np.ndarray, n: int):
     return ipiv, info
 
 
+def getri_outofplace_batched(LU: np.ndarray, ipiv: np.ndarray, n: int) -> np.ndarray:
+    """inv(A) per matrix from the factors (src/zgetri_outofplace_batched.cpp:114-135: identity, unit-lower solve,
+    upper solve, column interchanges in reverse). Column j of that product is U^-1 L^-1 e_pi(j), which is the solve
+    A X = I with the interchanges applied to the identity first: oracle_dgetrs on the identity, same arithmetic.
+    LU is (batch, n, ld) in the stored (column-major) layout of getrf_batched; the result is (batch, n, n)."""
+    batch = LU.shape[0]
+    eye = np.ascontiguousarray(np.broadcast_to(np.eye(n), (batch, n, n)))
+    getrs_batched(111, LU, ipiv, eye, n)  # in place
+    return eye
+
+
 def lu_backward_error(A0: np.ndarray, LU: np.ndarray, ipiv: np.ndarray, m: int) -> float:
     """max over the batch of ||P A0 - L U||_F / (||A0||_F n)."""
     batch, n, ld0 = A0.shape

@@ -289,6 +289,34 @@ def test_getrs(gpu_queue, trans, n, nrhs):
     assert oracle.solve_residual(trans, A0, X, B0, n) < oracle.TOL
 
 
+@pytest.mark.parametrize("n,batch", [(1, 5), (7, 9), (16, 33), (32, 12), (33, 7), (75, 5), (128, 4), (200, 3), (300, 2)])
+def test_getri_outofplace(gpu_queue, n, batch):
+    """magma_dgetri_outofplace_batched: bit-identical to the oracle's solve on the identity,
+    and the reference tester's check ||I - A inv(A)|| small (testing/testing_zgetri_batched.cpp)."""
+    A0, _ = oracle.random_batch(batch, n, n)
+    db = mb.DeviceBatch(batch, n, n, nrhs=n, queue=gpu_queue)
+    db.upload(A0, np.full((batch, n, n), 7.0))  # stale contents must be overwritten
+    assert db.getrf() == 0
+    assert mb.magma_dgetri_outofplace_batched(n, db.dA_array, db.ldda, db.dipiv_array, db.dB_array, db.lddb,
+                                              db.info, batch, gpu_queue) == 0
+    LU, ipiv, info, X = db.download()
+    assert not info.any()
+    Xr = oracle.getri_outofplace_batched(LU, ipiv, n)
+    assert np.array_equal(X, Xr), f"max diff {np.max(np.abs(X - Xr))}"
+    # stored layout is [b][col][row]: A = A0[b].T, inv = X[b].T
+    for b in range(batch):
+        A, Ai = A0[b].T, X[b].T
+        r = np.linalg.norm(np.eye(n) - A @ Ai, 1) / (n * np.linalg.norm(A, 1) * np.linalg.norm(Ai, 1))
+        assert r < oracle.TOL
+
+
+def test_getri_argument_errors(gpu_queue):
+    assert mb.magma_dgetri_outofplace_batched(-1, None, 1, None, None, 1, None, 1, gpu_queue) == -1
+    assert mb.magma_dgetri_outofplace_batched(4, None, 3, None, None, 4, None, 1, gpu_queue) == -3
+    assert mb.magma_dgetri_outofplace_batched(4, None, 4, None, None, 3, None, 1, gpu_queue) == -6
+    assert mb.magma_dgetri_outofplace_batched(0, None, 1, None, None, 1, None, 1, gpu_queue) == 0
+
+
 # ---- variable-size batch ------------------------------------------------------------------------
 
 def _vbatched_case(q, ms, ns, lds=None, expert=False):

@@ -101,6 +101,23 @@ def test_getrs_trans_and_notrans_vs_lapack():
         assert oracle.solve_residual(trans, A, X, B, n) < oracle.TOL
 
 
+def test_getri_vs_lapack():
+    """oracle.getri_outofplace_batched against host LAPACK's inverse (numpy: dgesv on I) and
+    the reference tester's residual ||I - A inv(A)||_1 / (n ||A||_1 ||inv(A)||_1) (testing/testing_zgetri_batched.cpp)."""
+    for n, batch in ((1, 3), (9, 20), (40, 10), (130, 3)):
+        A, _ = oracle.random_batch(batch, n, n)
+        LU = A.copy()
+        ipiv, info = oracle.getrf_batched(LU, n)
+        assert not info.any()
+        X = oracle.getri_outofplace_batched(LU, ipiv, n)
+        for b in range(batch):
+            Ab, Xb = A[b].T, X[b].T  # stored layout is [col][row]
+            ref = np.linalg.inv(Ab)
+            assert np.allclose(Xb, ref, rtol=1e-8, atol=1e-10 * np.max(np.abs(ref)))
+            r = np.linalg.norm(np.eye(n) - Ab @ Xb, 1) / (n * np.linalg.norm(Ab, 1) * np.linalg.norm(Xb, 1))
+            assert r < oracle.TOL
+
+
 def test_singular_and_tie_semantics():
     # zero matrix: info = 1, ipiv = identity, nothing scaled (smallsq_noshfl.cu:90-91,106)
     Z = np.zeros((1, 5, 5))

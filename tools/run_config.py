@@ -11,6 +11,7 @@ do_getrs = len(sys.argv) > 5
 torch.cuda.set_device(0); mb.magma_init(); q = mb.Queue.from_torch(0)
 if os.environ.get("TIER"): mb.set_tier(int(os.environ["TIER"]))
 if os.environ.get("SMALL_ROWS"): mb.set_small_rows(int(os.environ["SMALL_ROWS"]))
+if os.environ.get("MID_MAX"): mb.set_mid_max(int(os.environ["MID_MAX"]))
 db = mb.DeviceBatch(batch, n, n, nrhs=nrhs, queue=q)
 seed = np.array([0, 0, 0, 1], dtype=np.int32)
 mb.dlarnv_uniform(seed, batch * n * n, db.A, q)

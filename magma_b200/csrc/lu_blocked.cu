@@ -39,8 +39,8 @@ static_assert(sizeof(PivRec) == 512, "PivRec layout");
 // -------------------------------------------------------------------------------------------
 // Panel factorisation, registers. Thread t owns panel rows t, t+T, ... (R of them), W columns.
 // -------------------------------------------------------------------------------------------
-template <int R, int W>
-__global__ void __launch_bounds__(512)
+template <int R, int W, int MAXT = 512, int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB)
 panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__restrict__ dinfo,
              PivRec *__restrict__ recs, int j, long batch, const int *__restrict__ index_list,
              unsigned short *__restrict__ sinv = nullptr, int sinv_rows = 0, int sinv_blocks = 0)
@@ -1353,6 +1353,30 @@ magma_int_t launch_gemm_dmma(const Dims &d, double **dA, int k0, int rs, int cs,
     return 0;
 }
 
+// 32-column register panel with T threads (one row each). Short panels get a register budget (80) that lets two
+// (<= 384 rows), three (<= 256), four (<= 192), six (<= 128) ... CTAs share an SM: the per-column pivot chain (~900 cycles) is latency, and
+// an SM fills it only with other panels.
+inline void launch_panel32(const Dims &d, double **dA, int **dipiv, int *dinfo, PivRec *recs, int j, int T, long batch,
+                           const int *il, cudaStream_t s, unsigned short *sinv = nullptr, int sinv_rows = 0,
+                           int sinv_blocks = 0)
+{
+    if (T <= 64)
+        panel_kernel<1, 32, 64, 12><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+    else if (T <= 96)
+        panel_kernel<1, 32, 96, 8><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+    else if (T <= 128)
+        panel_kernel<1, 32, 128, 6><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+    else if (T <= 192)
+        panel_kernel<1, 32, 192, 4><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+    else if (T <= 256)
+        panel_kernel<1, 32, 256, 3><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+    else if (T <= 384)
+        panel_kernel<1, 32, 384, 2><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+    else
+        panel_kernel<1, 32><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+    count_launch();
+}
+
 // Two 32-column panels as one 64-wide step (panels <= 512 rows, both in the tiled regime). The trailing
 // matrix is read and written ONCE per 64 columns instead of once per 32 (the k = 32 update was HBM bound:
 // 87 GB per n = 512 call):
@@ -1368,8 +1392,7 @@ magma_int_t run_pair(const Dims &d, int max_m, int max_n, double **dA, int **dip
     auto panel = [&](int jj) -> magma_int_t {
         int T = ((max_m - jj + 31) / 32) * 32;
         if (T > 512) return MAGMA_ERR_NOT_SUPPORTED;
-        panel_kernel<1, 32><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, jj, batch, il);
-        count_launch();
+        launch_panel32(d, dA, dipiv, dinfo, recs, jj, T, batch, il, s);
         MB200_CHECK_LAUNCH("panel_kernel");
         return 0;
     };
@@ -1406,9 +1429,14 @@ magma_int_t run_step(const Dims &d, int max_m, int max_n, double **dA, int **dip
         int T = (mp + R - 1) / R;
         T = ((T + 31) / 32) * 32;
         if (T > 512) return MAGMA_ERR_NOT_SUPPORTED;
-        panel_kernel<R, W><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il);
+        if constexpr (R == 1 && W == 32) {
+            launch_panel32(d, dA, dipiv, dinfo, recs, j, T, batch, il, s);
+        } else {
+            panel_kernel<R, W><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il);
+            count_launch();
+        }
     }
-    count_launch();
+    if (global_panel) count_launch();
     MB200_CHECK_LAUNCH("panel_kernel");
 
     // fixed size: the panel width is known here; variable size: a matrix on its last, narrower
@@ -1505,8 +1533,7 @@ magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, i
         const int j = 32 * J;
         if (j < max_mn) {
             const int T = ((max_m - j + 31) / 32) * 32;
-            panel_kernel<1, 32><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
-            count_launch();
+            launch_panel32(d, dA, dipiv, dinfo, recs, j, T, batch, il, s, sinv, sinv_rows, sinv_blocks);
             MB200_CHECK_LAUNCH("panel_kernel");
             // a last, narrower panel with columns to its right in the same slab (wide matrices). Variable sizes:
             // any panel may be some matrix's last one, the kernel sorts that out per matrix.

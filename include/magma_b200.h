@@ -310,11 +310,14 @@ double magma_b200_hbm_copy_gbs(size_t bytes, magma_queue_t queue);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t magma_b200_launch_count(void);
 /* Force a tier for tests/benches: 0 = auto, 1 = register/warp (small), 2 = blocked everywhere,
- * 4 = blocked tier and getrs on the DFMA kernels only (no tensor pipe), 5 = no 64-wide pairing. */
+ * 4 = blocked tier and getrs on the DFMA kernels only (no tensor pipe), 5 = no 64-wide pairing,
+ * 6 = right-looking blocked driver everywhere, 7 = left-looking slab driver up to 512 rows (default: 448). */
 void magma_b200_set_tier(int tier);
 /* Largest max(m,n) routed to the register-file tier (lu_mid.cu), 32..128; for tuning sweeps. */
 void magma_b200_set_mid_max(int n);
-/* Register tier layout override for tuning sweeps: rows per lane (1 or 2), 0 = tuned default. */
+/* Register tier layout override for tuning sweeps: rows per lane (1 or 2), 0 = tuned default; 3/4 = alternative
+ * square kernels (n = 32 staged / n = 16 with 4 CTAs per SM), 7 = keep the register-file tier on 65..96
+ * (default: left-looking blocked driver there), 8 = single-phase 16-warp register-file kernel, 9 = generic kernel only. */
 void magma_b200_set_small_rows(int rows);
 
 /* F77-style by-reference wrappers in the control/magma_df77.cpp convention (device pointers

@@ -294,13 +294,17 @@ static magma_int_t vbatched_run(magma_int_t *m, magma_int_t *n, int max_m, int m
         else rc = lu_blocked_launch(d, 32, 32, dA_array, ipiv_array, info_array, cnt[0], lists, recs, s);
     }
     static const int cap[3] = {64, 96, 128};
+    void *perm = vbatched_perm_bytes(batch) ? (char *)work + vbatched_base_bytes(batch) : nullptr;
     for (int c = 1; c <= 3 && rc == 0; ++c)
-        if (cnt[c] > 0)
+        if (cnt[c] > 0) {
             rc = lu_mid_launch(d, imin(max_m, cap[c - 1]), imin(max_n, cap[c - 1]), dA_array, ipiv_array, info_array,
                                cnt[c], lists + (size_t)c * batch, s);
+            if (rc == -100)  // the register-file tier hands the 65..96 window to the left-looking blocked driver
+                rc = lu_blocked_launch(d, imin(max_m, cap[c - 1]), imin(max_n, cap[c - 1]), dA_array, ipiv_array, info_array,
+                                       cnt[c], lists + (size_t)c * batch, recs, s, perm);
+        }
     // blocked tier, one step sequence per size class (the pivot records are reused: the stream serialises them)
     static const int bcap[3] = {256, 384, 0x7fffffff};
-    void *perm = vbatched_perm_bytes(batch) ? (char *)work + vbatched_base_bytes(batch) : nullptr;
     for (int c = 4; c <= 6 && rc == 0; ++c)
         if (cnt[c] > 0)
             rc = lu_blocked_launch(d, imin(max_m, bcap[c - 4]), imin(max_n, bcap[c - 4]), dA_array, ipiv_array, info_array,

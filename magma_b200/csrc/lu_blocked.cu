@@ -1504,10 +1504,10 @@ size_t lu_blocked_workspace_bytes(long batch) { return sizeof(PivRec) * (size_t)
 size_t lu_blocked_perm_bytes(long batch, int max_m, int max_n)
 {
     const int mn = max_m < max_n ? max_m : max_n;
-    // more than 384 rows: one CTA per SM (16 warps x 128 registers) cannot overlap its solve / load phases with the
-    // tensor-pipe phase and is level with the right-looking flow (n = 512: 43.7 vs 43.1 ms; n = 384: 37.9 vs 38.8;
+    // more than 448 rows: one CTA per SM (16 warps x 128 registers) cannot overlap its solve / load phases with the
+    // tensor-pipe phase and is level with the right-looking flow (n = 512: 41.9 vs 41.5 ms; n = 448: 38.3 vs 39.3;
     // profiles/README.md); tier 7 forces it
-    if (batch <= 0 || max_n <= 32 || max_m > 512 || (max_m > 384 && g_tier != 7)) return 0;
+    if (batch <= 0 || max_n <= 32 || max_m > 512 || (max_m > 448 && g_tier != 7)) return 0;
     const size_t rows = (size_t)((max_m + 31) / 32) * 32, blocks = (size_t)(mn + 31) / 32;
     return sizeof(unsigned short) * rows * blocks * (size_t)batch;
 }
@@ -1563,7 +1563,7 @@ magma_int_t lu_blocked_launch(const Dims &d, int max_m, int max_n, double **dA, 
     PivRec *recs = reinterpret_cast<PivRec *>(workspace);
     const int max_mn = max_m < max_n ? max_m : max_n;  // upper bound of min(m_b, n_b)
     // tiers 4 (DFMA only), 5 (no pairing), 6 (right-looking) keep the right-looking flow for A/B runs
-    if (perm_workspace && max_n > 32 && (max_m <= 384 || (max_m <= 512 && g_tier == 7)) && g_tier != 4 && g_tier != 5 &&
+    if (perm_workspace && max_n > 32 && (max_m <= 448 || (max_m <= 512 && g_tier == 7)) && g_tier != 4 && g_tier != 5 &&
         g_tier != 6)
         return run_left_looking(d, max_m, max_n, dA, dipiv, dinfo, recs, reinterpret_cast<unsigned short *>(perm_workspace),
                                 batch, index_list, s);

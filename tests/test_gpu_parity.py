@@ -135,7 +135,9 @@ def test_getrf_blocked_ldda(gpu_queue, n, ldda):
 @pytest.fixture
 def mid_tier_128():
     mb.set_mid_max(128)
+    mb.set_small_rows(7)   # keep the register-file tier on 65..96 too (default: left-looking blocked driver there)
     yield
+    mb.set_small_rows(0)
     mb.set_mid_max(128)
 
 

@@ -1332,6 +1332,59 @@ magma_int_t launch_left_update(const Dims &d, double **dA, const unsigned short 
     return 0;
 }
 
+// -------------------------------------------------------------------------------------------
+// Deferred interchanges of the L part when the step permutations are on record (left-looking driver):
+// one CTA per (matrix, column block J, group of 8 columns), thread = row. The source row of every
+// final position comes from walking the recorded permutations back (nk - J - 1 table look-ups in
+// shared memory, all rows in parallel) instead of replaying up to 480 interchanges on one thread;
+// each thread holds its 8 values in registers across ONE barrier (all reads of a column precede all
+// writes), rows that did not move are neither read nor written.
+// -------------------------------------------------------------------------------------------
+constexpr int LSP_COLS = 8;
+
+__global__ void __launch_bounds__(512)
+laswp_left_sinv_kernel(Dims d, double **__restrict__ dA, const unsigned short *__restrict__ sinv_g, int sinv_rows,
+                       int sinv_blocks, int blocks, long batch, const int *__restrict__ index_list)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned short *tab = reinterpret_cast<unsigned short *>(smem_raw);  // [later panels][sinv_rows]
+
+    constexpr int GROUPS = 32 / LSP_COLS;
+    const int grp = blockIdx.x % GROUPS;
+    const int J = (blockIdx.x / GROUPS) % blocks;
+    const long slot = blockIdx.x / (GROUPS * blocks);
+    const long b = index_list ? index_list[slot] : slot;
+    if (b < 0) return;
+    int m, n, ld;
+    dims_of(d, b, m, n, ld);
+    const int mn = m < n ? m : n;
+    const int nk = (mn + 31) >> 5;  // panels of this matrix
+    if (J + 1 >= nk) return;        // no later panel: nothing to apply
+    const int r0 = 32 * (J + 1);
+    const int rows = m - r0;
+    const int tid = threadIdx.x;
+    const unsigned short *sg = sinv_g + (size_t)slot * sinv_blocks * sinv_rows;
+    for (int K = J + 1; K < nk; ++K)
+        for (int i = tid; i < m; i += blockDim.x) tab[(K - J - 1) * sinv_rows + i] = sg[(size_t)K * sinv_rows + i];
+    __syncthreads();
+    int r = r0 + tid;
+    const bool live = tid < rows;
+    if (live) {
+        for (int K = nk - 1; K > J; --K)
+            if (r >= 32 * K) r = tab[(K - J - 1) * sinv_rows + r];
+    }
+    const bool moved = live && (r != r0 + tid);
+    double *__restrict__ A = dA[b] + (size_t)(32 * J + LSP_COLS * grp) * ld;
+    double v[LSP_COLS];
+#pragma unroll
+    for (int c = 0; c < LSP_COLS; ++c) v[c] = moved ? A[r + (size_t)c * ld] : 0.0;
+    __syncthreads();
+    if (moved) {
+#pragma unroll
+        for (int c = 0; c < LSP_COLS; ++c) A[r0 + tid + (size_t)c * ld] = v[c];
+    }
+}
+
 // C[rs.., cs..climit) -= A[:, k0..k0+KW) * A[k0..k0+KW, :) over at most rows_max x cols_max per matrix
 template <int KW>
 magma_int_t launch_gemm_dmma(const Dims &d, double **dA, int k0, int rs, int cs, int climit, int rows_max, int cols_max,
@@ -1542,14 +1595,14 @@ magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, i
         }
     }
     if (max_mn > 32) {
-        const int blocks = (max_mn - 1) / 32;
-        const int max_rows = max_m - 32;
-        const size_t smem = sizeof(int) * 2 * (size_t)max_rows + 16 + sizeof(double) * LSWP_COLS * (size_t)max_rows;
-        const long grid = (long)blocks * batch;
+        const int blocks = (max_mn - 1) / 32;  // column blocks that have a later panel
+        const int T = ((max_m - 32 + 31) / 32) * 32;
+        const size_t smem = sizeof(unsigned short) * (size_t)sinv_rows * (size_t)(sinv_blocks - 1);
+        const long grid = (long)blocks * batch * (32 / LSP_COLS);
         if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
-        laswp_left_kernel<<<(unsigned)grid, LSWP_THREADS, smem, s>>>(d, dA, dipiv, blocks, max_rows, 32, 0, batch, il);
+        laswp_left_sinv_kernel<<<(unsigned)grid, T, smem, s>>>(d, dA, sinv, sinv_rows, sinv_blocks, blocks, batch, il);
         count_launch();
-        MB200_CHECK_LAUNCH("laswp_left_kernel");
+        MB200_CHECK_LAUNCH("laswp_left_sinv_kernel");
     }
     return 0;
 }

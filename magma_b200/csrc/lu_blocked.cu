@@ -1050,11 +1050,12 @@ constexpr int LL_CHUNK = 8 * LL_LDA;  // doubles per chunk: 8 k-columns x (4 til
 
 template <int NW>
 struct LeftSmem {
-    static constexpr int RING = (NW == 16) ? 4 : 3;  // chunks per warp (RING - 1 in flight)
+    static constexpr int RING = (NW == 4) ? 3 : 4;  // chunks per warp (RING - 1 in flight)
     double Us[32 * LL_LDU];                 // block row K of the slab as the owners left it
-    double Un[2][32 * LL_LDU];              // -U(K, J), double buffered (the update of step K reads it while
-                                            // the solve of step K+1 writes the other one)
-    double Ls[2][32 * 33];                  // L_KK, prefetched one step ahead
+    double Un[32 * LL_LDU];                 // -U(K, J): written by the solve of step K (between the step's two
+                                            // barriers), read by its ring pass; every warp is past that pass when
+                                            // the next solve starts, so one buffer is enough
+    double Ls[32 * 33];                     // L_KK: read by the solve, refilled (cp.async) during the ring pass
     unsigned short rmap[NW][NW * 32];       // row i of the current order -> row in the order of panel K
     unsigned short src[NW * 32];            // row i of the current order -> original row (slab load)
     double ring[NW * RING * LL_CHUNK];      // per-warp private L chunks (cp.async); the staged step
@@ -1062,7 +1063,7 @@ struct LeftSmem {
 };
 
 template <int NW>
-__global__ void __launch_bounds__(NW * 32, NW == 16 ? 1 : 2)
+__global__ void __launch_bounds__(NW * 32, NW == 16 ? 1 : (NW == 8 ? 2 : 4))
 left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__restrict__ sinv_g, int sinv_rows,
                    int sinv_blocks, int J, int finish, long batch, const int *__restrict__ index_list)
 {
@@ -1169,7 +1170,7 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
         for (int idx = tid; idx < 1024; idx += T) {
             const int i = idx & 31, k = idx >> 5;
             const bool ok = (i < kbK && k < kbK);
-            cp_async8(&S.Ls[K & 1][i * 33 + k], ok ? LKK + i + (size_t)k * ld : A, ok);
+            cp_async8(&S.Ls[i * 33 + k], ok ? LKK + i + (size_t)k * ld : A, ok);
         }
     };
     stage_lkk(kfirst);
@@ -1217,32 +1218,63 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             }
         }
         __syncthreads();
-        // ---- U(K, J) = L_KK^-1 * block row: column 4w+q, rows g, g+8, g+16, g+24 per lane ----------------------
-        if (w < 8) {
-            const int cc = 4 * w + q;
-            const double *Lk = S.Ls[K & 1];
-            double x[4];
+        // ---- U(K, J) = L_KK^-1 * block row ----------------------------------------------------------------------
+        if (NW >= 8) {
+            // eight warps: column 4w+q, rows g, g+8, g+16, g+24 per lane
+            if (w < 8) {
+                const int cc = 4 * w + q;
+                const double *Lk = S.Ls;
+                double x[4];
 #pragma unroll
-            for (int sblk = 0; sblk < 4; ++sblk) x[sblk] = S.Us[(g + 8 * sblk) * LL_LDU + cc];
+                for (int sblk = 0; sblk < 4; ++sblk) x[sblk] = S.Us[(g + 8 * sblk) * LL_LDU + cc];
 #pragma unroll
-            for (int k = 0; k < 31; ++k) {
-                const double u = __shfl_sync(FULLM, x[k >> 3], ((k & 7) << 2) | q);
+                for (int k = 0; k < 31; ++k) {
+                    const double u = __shfl_sync(FULLM, x[k >> 3], ((k & 7) << 2) | q);
+#pragma unroll
+                    for (int sblk = 0; sblk < 4; ++sblk) {
+                        if (8 * sblk + 7 > k) {  // static: this row group still has rows below k
+                            const int i = g + 8 * sblk;
+                            const double l = Lk[i * 33 + k];
+                            if (i > k) x[sblk] = fma(-l, u, x[sblk]);
+                        }
+                    }
+                }
+                const bool cok = (cc >= cb && cc < nc);
+                double *Un = S.Un;
 #pragma unroll
                 for (int sblk = 0; sblk < 4; ++sblk) {
-                    if (8 * sblk + 7 > k) {  // static: this row group still has rows below k
-                        const int i = g + 8 * sblk;
+                    const int i = g + 8 * sblk;
+                    Un[i * LL_LDU + cc] = -x[sblk];
+                    if (cok && i < kb) A[(size_t)(32 * K + i) + (size_t)(c0 + cc) * ld] = x[sblk];  // final rows of U
+                }
+            }
+        } else {
+            // four warps (at most 128 rows): column 8w + lane%8, rows lane/8 + 4i (i < 8) per lane
+            const int cl = lane & 7, rg = lane >> 3;
+            const int cc = 8 * w + cl;
+            const double *Lk = S.Ls;
+            double x[8];
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) x[i8] = S.Us[(rg + 4 * i8) * LL_LDU + cc];
+#pragma unroll
+            for (int k = 0; k < 31; ++k) {
+                const double u = __shfl_sync(FULLM, x[k >> 2], ((k & 3) << 3) | cl);
+#pragma unroll
+                for (int i8 = 0; i8 < 8; ++i8) {
+                    if (4 * i8 + 3 > k) {
+                        const int i = rg + 4 * i8;
                         const double l = Lk[i * 33 + k];
-                        if (i > k) x[sblk] = fma(-l, u, x[sblk]);
+                        if (i > k) x[i8] = fma(-l, u, x[i8]);
                     }
                 }
             }
             const bool cok = (cc >= cb && cc < nc);
-            double *Un = S.Un[K & 1];
+            double *Un = S.Un;
 #pragma unroll
-            for (int sblk = 0; sblk < 4; ++sblk) {
-                const int i = g + 8 * sblk;
-                Un[i * LL_LDU + cc] = -x[sblk];
-                if (cok && i < kb) A[(size_t)(32 * K + i) + (size_t)(c0 + cc) * ld] = x[sblk];  // final rows of U
+            for (int i8 = 0; i8 < 8; ++i8) {
+                const int i = rg + 4 * i8;
+                Un[i * LL_LDU + cc] = -x[i8];
+                if (cok && i < kb) A[(size_t)(32 * K + i) + (size_t)(c0 + cc) * ld] = x[i8];
             }
         }
         __syncthreads();
@@ -1250,7 +1282,7 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
         // A warp's tiles leave the active region in order (a = 0 first): the pass is specialised on the number
         // of tiles already out. (With a per-tile `if` ptxas predicates the DMMAs instead of branching, and a
         // predicated-off DMMA still occupies the tensor pipe: half of its cycles in the late slabs.)
-        const double *Un = S.Un[K & 1];
+        const double *Un = S.Un;
         auto ring_pass = [&](auto amin_c) {
             constexpr int AMIN = decltype(amin_c)::value;
             bool on[4];
@@ -1576,6 +1608,7 @@ magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, i
     const int sinv_rows = ((max_m + 31) / 32) * 32, sinv_blocks = (max_mn + 31) / 32;
     const int slabs = (max_n + 31) / 32;
     auto left = [&](int J, int finish) -> magma_int_t {
+        if (max_m <= 128) return launch_left_update<4>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, batch, il, s);
         return (max_m <= 256) ? launch_left_update<8>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, batch, il, s)
                               : launch_left_update<16>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, batch, il, s);
     };

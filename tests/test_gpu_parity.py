@@ -192,6 +192,19 @@ def test_left_looking_16_warps(gpu_queue, m, n, batch):
         mb.set_tier(0)
 
 
+@pytest.mark.parametrize("m,n,batch", [(33, 33, 21), (64, 64, 9), (65, 65, 9), (80, 80, 5), (96, 96, 7), (100, 100, 5),
+                                       (128, 128, 6), (128, 40, 5), (40, 128, 5), (97, 90, 4), (33, 128, 3), (128, 33, 3),
+                                       (127, 121, 3), (70, 200, 3), (100, 37, 4)])
+def test_left_looking_4_warps(gpu_queue, m, n, batch):
+    """The left-looking driver with 4 warps per slab (at most 128 rows): default for 65..96, forced here for 33..128."""
+    mb.set_mid_max(32)
+    try:
+        A0, _ = oracle.random_batch(batch, m, n)
+        check_against_oracle(gpu_queue, A0, m)
+    finally:
+        mb.set_mid_max(128)
+
+
 @pytest.mark.parametrize("m,n,batch", [(200, 200, 4), (256, 256, 3), (70, 300, 4), (150, 40, 5)])
 def test_right_looking_forced(gpu_queue, m, n, batch):
     """Tier 6: the right-looking flow on shapes the left-looking driver takes by default."""

@@ -397,12 +397,12 @@ magma_int_t lu_mid_launch(const Dims &d, int max_m, int max_n, double **dA, int 
     if (batch <= 0) return 0;
     if (max_m > 128 || max_n > 128) return -100;
     {
-        // max(m, n) > 48: the left-looking slab driver of the blocked tier is ahead (per 50000*128^2-equivalent batch:
-        // n = 128 12.4 vs 15.2 ms, n = 96 10.9 vs 18.7, n = 64 9.8 vs 11.5, n = 48 level) -- short panels with 6..12 CTAs
+        // max(m, n) > 44: the left-looking slab driver of the blocked tier is ahead (per 50000*128^2-equivalent batch:
+        // n = 128 12.2 vs 15.2 ms, n = 96 10.7 vs 18.7, n = 64 9.6 vs 11.5, n = 48 13.7 vs 14.4; n = 40 17.9 vs 16.3) -- short panels with 6..12 CTAs
         // per SM and 4-warp slab updates beat one pivot chain per matrix. magma_b200_set_small_rows(7) keeps this
         // tier up to 128 (A/B runs, tests).
         const int mx = max_m > max_n ? max_m : max_n;
-        if (mx > 48 && g_small_rows != 7 && g_small_rows != 8) return -100;
+        if (mx > 44 && g_small_rows != 7 && g_small_rows != 8) return -100;
     }
     if (g_small_rows == 8) {  // the single-phase 16-warp kernel (A/B runs)
         if (max_m <= 64 && max_n <= 64) return launch_mid<2, 8, 1, 3>(d, dA, dipiv, dinfo, batch, index_list, s);

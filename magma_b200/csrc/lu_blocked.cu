@@ -1045,12 +1045,36 @@ laswp_left_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, in
 // balanced); lane (g = lane/4, q = lane%4) holds C(8t+g, 8c+2q) and C(8t+g, 8c+2q+1).
 // -------------------------------------------------------------------------------------------
 constexpr int LL_LDU = 36;  // Us[k*LL_LDU + c]: B fragments (k = 4s+q, c = 8ct+g) hit 32 distinct banks
-constexpr int LL_LDA = 36;  // ring chunk: As[kk*LL_LDA + 8a+g], same property for the A fragments
-constexpr int LL_CHUNK = 8 * LL_LDA;  // doubles per chunk: 8 k-columns x (4 tiles x 8 rows + pad)
+
+// mbarrier helpers of the L chunk pipeline
+__device__ __forceinline__ void ll_mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ll_mbar_arrive(void *bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void ll_mbar_arrive_cp_async(void *bar)  // arrives when this thread's earlier cp.asyncs have landed
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void ll_mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "LLWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+        "@!p bra LLWAIT_%=;\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
 
 template <int NW>
 struct LeftSmem {
-    static constexpr int RING = (NW == 4) ? 3 : 4;  // chunks per warp (RING - 1 in flight)
+    static constexpr int RING = (NW == 4) ? 3 : 4;  // chunks in the ring (RING - 1 in flight)
+    static constexpr int LDR = NW * 32 + 4;         // As[kk*LDR + row]: A fragments (k = 4s+q, row 8t+g) hit 32 distinct banks
     double Us[32 * LL_LDU];                 // block row K of the slab as the owners left it
     double Un[32 * LL_LDU];                 // -U(K, J): written by the solve of step K (between the step's two
                                             // barriers), read by its ring pass; every warp is past that pass when
@@ -1058,8 +1082,9 @@ struct LeftSmem {
     double Ls[32 * 33];                     // L_KK: read by the solve, refilled (cp.async) during the ring pass
     unsigned short rmap[NW][NW * 32];       // row i of the current order -> row in the order of panel K
     unsigned short src[NW * 32];            // row i of the current order -> original row (slab load)
-    double ring[NW * RING * LL_CHUNK];      // per-warp private L chunks (cp.async); the staged step
-                                            // permutations (NW x NW*32 shorts) live here during set-up
+    unsigned long long full[RING], empty[RING], lsbar;
+    alignas(16) double ring[RING * 8 * LDR];  // L chunks, CTA-wide, rows in the order of their own panel; the staged
+                                            // step permutations (NW x NW*32 shorts) live here during set-up
 };
 
 template <int NW>
@@ -1073,7 +1098,7 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
     LeftSmem<NW> &S = *reinterpret_cast<LeftSmem<NW> *>(smem_raw);
     constexpr int T = NW * 32;
     constexpr int RING = LeftSmem<NW>::RING;
-    static_assert(sizeof(unsigned short) * NW * T <= sizeof(double) * NW * RING * LL_CHUNK, "sinv overlay");
+    static_assert(sizeof(unsigned short) * NW * T <= sizeof(double) * RING * 8 * LeftSmem<NW>::LDR, "sinv overlay");
     const unsigned FULLM = 0xffffffffu;
 
     const long slot = blockIdx.x;
@@ -1112,59 +1137,49 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
     }
     __syncthreads();  // maps complete; the ring may be overwritten
 
-    // ---- L chunk pipeline: chunk 4K+ch = columns 32K+8ch .. +8 of L, this warp's rows, gathered by rmap[K].
-    // Every lane copies exactly the elements its own A fragments will read (row 8a+g, k 4s+q): no cross-lane
-    // hand-off, cp.async.wait_group is the only synchronisation.
-    double *myring = S.ring + (size_t)w * RING * LL_CHUNK;
-    const unsigned ring_lane = (unsigned)__cvta_generic_to_shared(myring + q * LL_LDA + g);  // + slot, kk, tile offsets
-    int roff[4];      // row of L (order of panel issue_K) behind each of this lane's four tile rows
-    int issue_K = -1;
-    auto issue = [&](int nchunk, int slot_in_ring) {
-        const int K = nchunk >> 2, ch = nchunk & 3;
-        if (K >= nk) return;
-        if (K != issue_K) {
-            issue_K = K;
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const int row = 8 * (w + NW * a) + g;
-                roff[a] = (row < m) ? (int)S.rmap[K][row] : 0;  // rows past m: any valid address, never stored
-            }
-        }
-        const int kbK = (kend - 32 * K) < 32 ? (kend - 32 * K) : 32;
-        const unsigned dst = ring_lane + (unsigned)(slot_in_ring * LL_CHUNK * 8);
-        const double *col0 = A + (size_t)(32 * K + 8 * ch + q) * ld;
-        if (kbK == 32) {
-#pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-                const double *colp = col0 + (size_t)(4 * s2) * ld;
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const int t = w + NW * a;
-                    if (t > 4 * K + 3 && 8 * t < m)  // warp-uniform: the tile lies below block row K
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (unsigned)((4 * s2 * LL_LDA + 8 * a) * 8)),
-                                     "l"(colp + roff[a])
+    // ---- L chunk pipeline: chunk 4K+ch = columns 32K+8ch .. +8 of L, every row below block row K, copied in the
+    // row order of panel K itself: contiguous 16-byte cp.asyncs (the first version gathered each warp's rows through
+    // rmap with 8-byte copies: 11 tag requests and 14 sectors per warp instruction instead of 4 and 16 for twice the
+    // bytes, 63% of all LSU wavefronts of the kernel). The permutation is applied when the A fragments are READ from
+    // shared memory (rmap, word granular). Slots are handed over with mbarriers: full[] counts the threads'
+    // cp.async completions, empty[] the threads that are done reading.
+    constexpr int LDR = LeftSmem<NW>::LDR;
+    const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    auto issue = [&](int nrel) {  // nrel: chunk number counted from the first step
+        const int K = kfirst + (nrel >> 2), ch = nrel & 3;
+        const int slot_r = nrel % RING;
+        if (nrel >= RING) ll_mbar_wait(&S.empty[slot_r], (unsigned)((nrel / RING - 1) & 1));
+        if (K < nk) {
+            const int kbK = (kend - 32 * K) < 32 ? (kend - 32 * K) : 32;
+            const int rlo = 32 * (K + 1);                     // even
+            double *dst = S.ring + (size_t)slot_r * 8 * LDR;
+            const double *colbase = A + (size_t)(32 * K + 8 * ch) * ld;
+            if (rlo < m) {
+                if (vec_ok) {
+                    const int npairs = (m - rlo + 1) >> 1;
+                    for (int u = tid; u < 8 * npairs; u += T) {
+                        const int kk = u / npairs, r = rlo + 2 * (u - kk * npairs);
+                        const bool kok = (8 * ch + kk) < kbK;
+                        const int bytes = kok ? ((r + 1 < m) ? 16 : 8) : 0;
+                        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + kk * LDR + r);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa),
+                                     "l"(kok ? colbase + (size_t)kk * ld + r : A), "r"(bytes)
                                      : "memory");
-                }
-            }
-        } else {  // last, narrower panel of a wide matrix: zero-fill the missing k
-#pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-                const bool kok = (8 * ch + 4 * s2 + q) < kbK;
-                const double *colp = kok ? col0 + (size_t)(4 * s2) * ld : A;
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const int t = w + NW * a;
-                    if (t > 4 * K + 3 && 8 * t < m) {
-                        const int sz = kok ? 8 : 0;
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + (unsigned)((4 * s2 * LL_LDA + 8 * a) * 8)),
-                                     "l"(colp + (kok ? roff[a] : 0)), "r"(sz)
-                                     : "memory");
+                    }
+                } else {
+                    const int nr = m - rlo;
+                    for (int u = tid; u < 8 * nr; u += T) {
+                        const int kk = u / nr, r = rlo + (u - kk * nr);
+                        const bool kok = (8 * ch + kk) < kbK;
+                        cp_async8(dst + kk * LDR + r, kok ? colbase + (size_t)kk * ld + r : A, kok);
                     }
                 }
             }
         }
+        ll_mbar_arrive_cp_async(&S.full[slot_r]);
     };
-    auto stage_lkk = [&](int K) {  // L_KK -> Ls[K & 1], zero outside the panel width
+    int ls_uses = 0;  // completed uses of lsbar
+    auto stage_lkk = [&](int K) {  // L_KK -> Ls, zero outside the panel width
         const int kbK = (kend - 32 * K) < 32 ? (kend - 32 * K) : 32;
         const double *LKK = A + (size_t)(32 * K) + (size_t)(32 * K) * ld;
         for (int idx = tid; idx < 1024; idx += T) {
@@ -1172,13 +1187,20 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             const bool ok = (i < kbK && k < kbK);
             cp_async8(&S.Ls[i * 33 + k], ok ? LKK + i + (size_t)k * ld : A, ok);
         }
+        ll_mbar_arrive_cp_async(&S.lsbar);
     };
+    if (tid == 0) {
+        for (int i = 0; i < RING; ++i) {
+            ll_mbar_init(&S.full[i], T);
+            ll_mbar_init(&S.empty[i], T);
+        }
+        ll_mbar_init(&S.lsbar, T);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     stage_lkk(kfirst);
 #pragma unroll
-    for (int pch = 0; pch < RING - 1; ++pch) {
-        issue(4 * kfirst + pch, pch);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
+    for (int pch = 0; pch < RING - 1; ++pch) issue(pch);
 
     // ---- the slab, rows in current order ---------------------------------------------------------------------
     double acc[4][4][2];
@@ -1194,10 +1216,9 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             acc[a][c][1] = (rok && col + 1 >= cb && col + 1 < nc) ? src[(size_t)(8 * c + 1) * ld] : 0.0;
         }
     }
-    asm volatile("cp.async.wait_group %0;" ::"n"(RING - 2) : "memory");  // first group: L_KK of the first step
     __syncthreads();  // every row is in registers: stores into the slab may begin
 
-    int rslot = 0;  // ring slot of the chunk consumed next
+    int nrel = 0;  // chunk consumed next, counted from the first step
 #pragma unroll 1
     for (int K = kfirst; K < nk; ++K) {
         const int kb = (kend - 32 * K) < 32 ? (kend - 32 * K) : 32;
@@ -1219,6 +1240,8 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
         }
         __syncthreads();
         // ---- U(K, J) = L_KK^-1 * block row ----------------------------------------------------------------------
+        if (NW < 8 || w < 8) ll_mbar_wait(&S.lsbar, (unsigned)(ls_uses & 1));  // L_KK has landed
+        ++ls_uses;
         if (NW >= 8) {
             // eight warps: column 4w+q, rows g, g+8, g+16, g+24 per lane
             if (w < 8) {
@@ -1283,6 +1306,13 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
         // of tiles already out. (With a per-tile `if` ptxas predicates the DMMAs instead of branching, and a
         // predicated-off DMMA still occupies the tensor pipe: half of its cycles in the late slabs.)
         const double *Un = S.Un;
+        // this lane's four tile rows in the row order of panel K (where the chunk's rows sit in shared memory)
+        int roff[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int row = 8 * (w + NW * a) + g;
+            roff[a] = (row < m) ? (int)S.rmap[K][row] : 32 * (K + 1);  // rows past m: any row of the chunk
+        }
         auto ring_pass = [&](auto amin_c) {
             constexpr int AMIN = decltype(amin_c)::value;
             bool on[4];
@@ -1290,16 +1320,12 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             for (int a = 0; a < 4; ++a) on[a] = (a >= AMIN) && (8 * (w + NW * a) < m);  // rows past m: predicated
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {
-                {
-                    int islot = rslot + RING - 1;
-                    if (islot >= RING) islot -= RING;
-                    issue(4 * K + ch + RING - 1, islot);
-                    if (ch == 0 && K + 1 < nk) stage_lkk(K + 1);
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                    asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory");
-                }
+                issue(nrel + RING - 1);
+                if (ch == 0 && K + 1 < nk) stage_lkk(K + 1);
+                const int slot_r = nrel % RING;
+                ll_mbar_wait(&S.full[slot_r], (unsigned)((nrel / RING) & 1));
                 if (AMIN < 4) {
-                    const double *As = myring + rslot * LL_CHUNK + q * LL_LDA + g;
+                    const double *As = S.ring + (size_t)slot_r * 8 * LDR + q * LDR;
 #pragma unroll
                     for (int s2 = 0; s2 < 2; ++s2) {
                         double bf[4];
@@ -1308,14 +1334,15 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
 #pragma unroll
                         for (int a = AMIN; a < 4; ++a) {
                             if (on[a]) {
-                                const double af = As[4 * s2 * LL_LDA + 8 * a];
+                                const double af = As[4 * s2 * LDR + roff[a]];
 #pragma unroll
                                 for (int c = 0; c < 4; ++c) dmma_884(acc[a][c][0], acc[a][c][1], af, bf[c]);
                             }
                         }
                     }
                 }
-                if (++rslot == RING) rslot = 0;
+                ll_mbar_arrive(&S.empty[slot_r]);  // after the DMMAs that consumed the fragments
+                ++nrel;
             }
         };
         {
@@ -1589,10 +1616,8 @@ size_t lu_blocked_workspace_bytes(long batch) { return sizeof(PivRec) * (size_t)
 size_t lu_blocked_perm_bytes(long batch, int max_m, int max_n)
 {
     const int mn = max_m < max_n ? max_m : max_n;
-    // more than 448 rows: one CTA per SM (16 warps x 128 registers) cannot overlap its solve / load phases with the
-    // tensor-pipe phase and is level with the right-looking flow (n = 512: 41.9 vs 41.5 ms; n = 448: 38.3 vs 39.3;
-    // profiles/README.md); tier 7 forces it
-    if (batch <= 0 || max_n <= 32 || max_m > 512 || (max_m > 448 && g_tier != 7)) return 0;
+    // every shape of at most 512 rows (tier 6 keeps the right-looking flow)
+    if (batch <= 0 || max_n <= 32 || max_m > 512) return 0;
     const size_t rows = (size_t)((max_m + 31) / 32) * 32, blocks = (size_t)(mn + 31) / 32;
     return sizeof(unsigned short) * rows * blocks * (size_t)batch;
 }
@@ -1649,7 +1674,7 @@ magma_int_t lu_blocked_launch(const Dims &d, int max_m, int max_n, double **dA, 
     PivRec *recs = reinterpret_cast<PivRec *>(workspace);
     const int max_mn = max_m < max_n ? max_m : max_n;  // upper bound of min(m_b, n_b)
     // tiers 4 (DFMA only), 5 (no pairing), 6 (right-looking) keep the right-looking flow for A/B runs
-    if (perm_workspace && max_n > 32 && (max_m <= 448 || (max_m <= 512 && g_tier == 7)) && g_tier != 4 && g_tier != 5 &&
+    if (perm_workspace && max_n > 32 && max_m <= 512 && g_tier != 4 && g_tier != 5 &&
         g_tier != 6)
         return run_left_looking(d, max_m, max_n, dA, dipiv, dinfo, recs, reinterpret_cast<unsigned short *>(perm_workspace),
                                 batch, index_list, s);

@@ -249,14 +249,14 @@ magma_int_t magma_dgesv_batched(magma_int_t n, magma_int_t nrhs, double **dA_arr
 // ---------------------------------------------------------------------------------------------
 static size_t vbatched_lists_bytes(long batch) { return (((size_t)(7 * batch + 8) * sizeof(int)) + 511) & ~(size_t)511; }
 // lists, pivot records, and (when the total still fits the int-sized lwork of the reference API) the
-// step-permutation records that let the <= 256 class run the left-looking driver
+// step-permutation records that let every class of at most 512 rows run the left-looking driver
 static size_t vbatched_base_bytes(long batch)
 {
     return (vbatched_lists_bytes(batch) + lu_blocked_workspace_bytes(batch) + 255) & ~(size_t)255;
 }
 static size_t vbatched_perm_bytes(long batch)
 {
-    const size_t p = lu_blocked_perm_bytes(batch, 256, 256);
+    const size_t p = lu_blocked_perm_bytes(batch, 512, 512);
     return (vbatched_base_bytes(batch) + p <= 0x7fffff00ull) ? p : 0;
 }
 static size_t vbatched_work_bytes(long batch) { return vbatched_base_bytes(batch) + vbatched_perm_bytes(batch); }
@@ -308,7 +308,7 @@ static magma_int_t vbatched_run(magma_int_t *m, magma_int_t *n, int max_m, int m
     for (int c = 4; c <= 6 && rc == 0; ++c)
         if (cnt[c] > 0)
             rc = lu_blocked_launch(d, imin(max_m, bcap[c - 4]), imin(max_n, bcap[c - 4]), dA_array, ipiv_array, info_array,
-                                   cnt[c], lists + (size_t)c * batch, recs, s, c == 4 ? perm : nullptr);
+                                   cnt[c], lists + (size_t)c * batch, recs, s, perm);
     return rc;
 }
 

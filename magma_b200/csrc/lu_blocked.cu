@@ -1073,7 +1073,7 @@ __device__ __forceinline__ void ll_mbar_wait(void *bar, unsigned parity)
 
 template <int NW>
 struct LeftSmem {
-    static constexpr int RING = (NW == 4) ? 3 : 4;  // chunks in the ring (RING - 1 in flight)
+    static constexpr int RING = (NW == 4) ? 3 : 4;  // chunks in the ring
     static constexpr int LDR = NW * 32 + 4;         // As[kk*LDR + row]: A fragments (k = 4s+q, row 8t+g) hit 32 distinct banks
     double Us[32 * LL_LDU];                 // block row K of the slab as the owners left it
     double Un[32 * LL_LDU];                 // -U(K, J): written by the solve of step K (between the step's two
@@ -1090,8 +1090,9 @@ struct LeftSmem {
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, NW == 16 ? 1 : (NW == 8 ? 2 : 4))
 left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__restrict__ sinv_g, int sinv_rows,
-                   int sinv_blocks, int J, int finish, long batch, const int *__restrict__ index_list)
+                   int sinv_blocks, int J, int finish, int ahead, long batch, const int *__restrict__ index_list)
 {
+    // ahead: chunks in flight (1 .. RING-1); a ring slot is refilled RING - ahead chunks after its last use.
     // finish = 1: second visit of the slab that holds the LAST, narrower panel of a wide matrix
     // (32J < min(m,n) < min(n, 32J+32)): its columns right of the panel still need that panel's step.
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1157,8 +1158,9 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             if (rlo < m) {
                 if (vec_ok) {
                     const int npairs = (m - rlo + 1) >> 1;
+                    const unsigned magic = 0xFFFFFFFFu / (unsigned)npairs + 1u;  // u / npairs == umulhi(u, magic) for npairs > 1 (u * npairs < 2^32)
                     for (int u = tid; u < 8 * npairs; u += T) {
-                        const int kk = u / npairs, r = rlo + 2 * (u - kk * npairs);
+                        const int kk = npairs > 1 ? (int)__umulhi((unsigned)u, magic) : u, r = rlo + 2 * (u - kk * npairs);
                         const bool kok = (8 * ch + kk) < kbK;
                         const int bytes = kok ? ((r + 1 < m) ? 16 : 8) : 0;
                         const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + kk * LDR + r);
@@ -1168,8 +1170,9 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
                     }
                 } else {
                     const int nr = m - rlo;
+                    const unsigned magic = 0xFFFFFFFFu / (unsigned)nr + 1u;
                     for (int u = tid; u < 8 * nr; u += T) {
-                        const int kk = u / nr, r = rlo + (u - kk * nr);
+                        const int kk = nr > 1 ? (int)__umulhi((unsigned)u, magic) : u, r = rlo + (u - kk * nr);
                         const bool kok = (8 * ch + kk) < kbK;
                         cp_async8(dst + kk * LDR + r, kok ? colbase + (size_t)kk * ld + r : A, kok);
                     }
@@ -1200,7 +1203,7 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
     __syncthreads();
     stage_lkk(kfirst);
 #pragma unroll
-    for (int pch = 0; pch < RING - 1; ++pch) issue(pch);
+    for (int pch = 0; pch < ahead; ++pch) issue(pch);
 
     // ---- the slab, rows in current order ---------------------------------------------------------------------
     double acc[4][4][2];
@@ -1320,7 +1323,7 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             for (int a = 0; a < 4; ++a) on[a] = (a >= AMIN) && (8 * (w + NW * a) < m);  // rows past m: predicated
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {
-                issue(nrel + RING - 1);
+                issue(nrel + ahead);
                 if (ch == 0 && K + 1 < nk) stage_lkk(K + 1);
                 const int slot_r = nrel % RING;
                 ll_mbar_wait(&S.full[slot_r], (unsigned)((nrel / RING) & 1));
@@ -1385,7 +1388,14 @@ magma_int_t launch_left_update(const Dims &d, double **dA, const unsigned short 
         cudaFuncSetAttribute(left_update_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    left_update_kernel<NW><<<(unsigned)batch, NW * 32, smem, s>>>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, batch, il);
+    static int ahead = -1;
+    if (ahead < 0) {
+        const char *e = getenv("MB200_LL_AHEAD");  // tuning sweeps
+        ahead = e ? atoi(e) : 2;  // measured: 1, 2, 3 within 3% of each other (n = 512: 34.5 / 34.4 / 35.6 ms)
+        if (ahead < 1) ahead = 1;
+        if (ahead > LeftSmem<NW>::RING - 1) ahead = LeftSmem<NW>::RING - 1;
+    }
+    left_update_kernel<NW><<<(unsigned)batch, NW * 32, smem, s>>>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, ahead, batch, il);
     count_launch();
     MB200_CHECK_LAUNCH("left_update_kernel");
     return 0;

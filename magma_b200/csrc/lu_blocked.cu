@@ -1159,14 +1159,21 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
                 if (vec_ok) {
                     const int npairs = (m - rlo + 1) >> 1;
                     const unsigned magic = 0xFFFFFFFFu / (unsigned)npairs + 1u;  // u / npairs == umulhi(u, magic) for npairs > 1 (u * npairs < 2^32)
-                    for (int u = tid; u < 8 * npairs; u += T) {
-                        const int kk = npairs > 1 ? (int)__umulhi((unsigned)u, magic) : u, r = rlo + 2 * (u - kk * npairs);
-                        const bool kok = (8 * ch + kk) < kbK;
-                        const int bytes = kok ? ((r + 1 < m) ? 16 : 8) : 0;
-                        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + kk * LDR + r);
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa),
-                                     "l"(kok ? colbase + (size_t)kk * ld + r : A), "r"(bytes)
-                                     : "memory");
+                    // at most 8 * (NW*16) / T = 4 copies per thread: unrolled, so that every copy has its own address
+                    // registers (LDGSTS holds them until it has read them: a rolled loop stalled on that hazard)
+                    const int total = 8 * npairs;
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int u = tid + it * T;
+                        if (u < total) {
+                            const int kk = npairs > 1 ? (int)__umulhi((unsigned)u, magic) : u, r = rlo + 2 * (u - kk * npairs);
+                            const bool kok = (8 * ch + kk) < kbK;
+                            const int bytes = kok ? ((r + 1 < m) ? 16 : 8) : 0;
+                            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + kk * LDR + r);
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa),
+                                         "l"(kok ? colbase + (size_t)kk * ld + r : A), "r"(bytes)
+                                         : "memory");
+                        }
                     }
                 } else {
                     const int nr = m - rlo;

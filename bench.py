@@ -121,6 +121,10 @@ def cpu_lapack_gesv(n, nrhs, batch_total, budget_s=12.0):
 
     import oracle
     L = oracle.lapack()
+    try:  # all the host threads this process may use (torchrun pins OMP_NUM_THREADS=1 in its workers)
+        L.lapack_loop_set_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
     cores = L.lapack_loop_threads()
     fl = flops_getrf(n, n) + flops_getrs(n, nrhs)
 

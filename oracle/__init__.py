@@ -94,6 +94,8 @@ def lapack():
         L.lapack_loop_init.restype = _i
         L.lapack_loop_describe.restype = C.c_char_p
         L.lapack_loop_threads.restype = _i
+        L.lapack_loop_set_threads.argtypes = [_i]
+        L.lapack_loop_set_threads.restype = None
         rc = L.lapack_loop_init(find_host_lapack().encode())
         if rc != 0:
             raise RuntimeError("lapack_loop_init: " + L.lapack_loop_describe().decode())

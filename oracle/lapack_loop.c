@@ -75,6 +75,16 @@ int lapack_loop_init(const char *libpath)
 
 const char *lapack_loop_describe(void) { return g_desc; }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the benchmark's reference arm asks for the box's cores back */
+void lapack_loop_set_threads(int nthreads)
+{
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+}
+
 int lapack_loop_threads(void)
 {
 #ifdef _OPENMP

@@ -217,6 +217,21 @@ magma_int_t magma_dgetri_outofplace_batched(magma_int_t n, double **dA_array, ma
                                             magma_int_t lddia, magma_int_t *info_array,
                                             magma_int_t batchCount, magma_queue_t queue);
 
+/* LU without pivoting and its solves.   src/zgetrf_nopiv_batched.cpp:75-170,
+ * src/zgetrs_nopiv_batched.cpp:85-180, src/zgesv_nopiv_batched.cpp:85-130; prototypes include/magma_zbatched.h:976-998.
+ * getrf: errors -1 m, -2 n, -4 ldda; info_array[b] = first i with U(i,i) == 0 (1-based), else 0. Unlike the reference,
+ * which stops factoring a matrix at its first zero diagonal, the factorisation is completed LAPACK-style (the zero
+ * pivot's column stays unscaled). At most 512 rows (MAGMA_ERR_NOT_SUPPORTED beyond).
+ * getrs: errors -1 trans, -2 n, -3 nrhs, -5 ldda, -8 lddb; gesv: -1 n, -2 nrhs, -4 ldda, -6 lddb. */
+magma_int_t magma_dgetrf_nopiv_batched(magma_int_t m, magma_int_t n, double **dA_array, magma_int_t ldda,
+                                       magma_int_t *info_array, magma_int_t batchCount, magma_queue_t queue);
+magma_int_t magma_dgetrs_nopiv_batched(magma_trans_t trans, magma_int_t n, magma_int_t nrhs, double **dA_array,
+                                       magma_int_t ldda, double **dB_array, magma_int_t lddb,
+                                       magma_int_t *info_array, magma_int_t batchCount, magma_queue_t queue);
+magma_int_t magma_dgesv_nopiv_batched(magma_int_t n, magma_int_t nrhs, double **dA_array, magma_int_t ldda,
+                                      double **dB_array, magma_int_t lddb, magma_int_t *info_array,
+                                      magma_int_t batchCount, magma_queue_t queue);
+
 /* Variable sizes; m, n, ldda are DEVICE arrays of length batchCount.
  * src/zgetrf_vbatched.cpp:340-398 (checker + setup + workspace inside, blocks the host). */
 magma_int_t magma_dgetrf_vbatched(magma_int_t *m, magma_int_t *n, double **dA_array, magma_int_t *ldda,

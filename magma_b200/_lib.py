@@ -70,6 +70,9 @@ SIGNATURES = {
     "magma_dgetrf_vbatched_max_nocheck": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp]),
     "magma_dgetrf_batched_smallsq_noshfl": (i32, [i32, vp, i32, vp, vp, i32, vp]),
     "magma_dgetri_outofplace_batched": (i32, [i32, vp, i32, vp, vp, i32, vp, i32, vp]),
+    "magma_dgetrf_nopiv_batched": (i32, [i32, i32, vp, i32, vp, i32, vp]),
+    "magma_dgetrs_nopiv_batched": (i32, [i32, i32, i32, vp, i32, vp, i32, vp, i32, vp]),
+    "magma_dgesv_nopiv_batched": (i32, [i32, i32, vp, i32, vp, i32, vp, i32, vp]),
     "magma_dgesv_batched_small": (i32, [i32, i32, vp, i32, vp, vp, i32, vp, i32, vp]),
     "magma_dlaswp_rowserial_batched": (None, [i32, vp, i32, i32, i32, vp, i32, vp]),
     "magmablas_dtrsm_batched": (None, [i32, i32, i32, i32, i32, i32, dbl, vp, i32, vp, i32, i32, vp]),

@@ -26,6 +26,7 @@ __all__ = [
     "MagmaUnit", "MagmaLeft", "MagmaRight", "Queue", "ptr", "magma_init", "magma_finalize",
     "magma_dgetrf_batched", "magma_dgetrs_batched", "magma_dgesv_batched", "magma_dgetrf_vbatched",
     "magma_dgetrf_vbatched_max_nocheck_work", "magma_dgetrf_batched_smallsq_noshfl", "magma_dgetri_outofplace_batched",
+    "magma_dgetrf_nopiv_batched", "magma_dgetrs_nopiv_batched", "magma_dgesv_nopiv_batched",
     "magma_dgesv_batched_small", "magma_dset_pointer", "magma_iset_pointer", "magma_ddisplace_pointers",
     "magma_dlaswp_rowserial_batched", "magmablas_dtrsm_batched", "magma_dgemm_batched_core",
     "magma_get_dgetrf_batched_nbparam", "dlarnv_uniform", "set_tier", "set_small_rows", "set_mid_max", "launch_count",
@@ -139,6 +140,20 @@ def magma_dgetri_outofplace_batched(n, dA_array, ldda, dipiv_array, dinvA_array,
     """inv(A) from the factors, out of place (src/zgetri_outofplace_batched.cpp:81)."""
     return _lib.load().magma_dgetri_outofplace_batched(n, ptr(dA_array), ldda, ptr(dipiv_array), ptr(dinvA_array),
                                                        lddia, ptr(info_array), batchCount, _q(queue))
+
+
+def magma_dgetrf_nopiv_batched(m, n, dA_array, ldda, info_array, batchCount, queue) -> int:
+    return _lib.load().magma_dgetrf_nopiv_batched(m, n, ptr(dA_array), ldda, ptr(info_array), batchCount, _q(queue))
+
+
+def magma_dgetrs_nopiv_batched(trans, n, nrhs, dA_array, ldda, dB_array, lddb, info_array, batchCount, queue) -> int:
+    return _lib.load().magma_dgetrs_nopiv_batched(trans, n, nrhs, ptr(dA_array), ldda, ptr(dB_array), lddb,
+                                                  ptr(info_array), batchCount, _q(queue))
+
+
+def magma_dgesv_nopiv_batched(n, nrhs, dA_array, ldda, dB_array, lddb, info_array, batchCount, queue) -> int:
+    return _lib.load().magma_dgesv_nopiv_batched(n, nrhs, ptr(dA_array), ldda, ptr(dB_array), lddb, ptr(info_array),
+                                                 batchCount, _q(queue))
 
 
 def magma_dgesv_batched_small(n, nrhs, dA_array, ldda, dipiv_array, dB_array, lddb, dinfo_array, batchCount,

@@ -197,6 +197,97 @@ magma_int_t magma_dgetrs_batched(magma_trans_t trans, magma_int_t n, magma_int_t
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// LU without pivoting.   src/zgetrf_nopiv_batched.cpp:75-170, src/zgetrs_nopiv_batched.cpp,
+// src/zgesv_nopiv_batched.cpp. Same kernels as the pivoted path: register panels with the diagonal as pivot,
+// left-looking slab updates; no interchange pass. At most 512 rows (the register panel's reach).
+// ---------------------------------------------------------------------------------------------
+magma_int_t magma_dgetrf_nopiv_batched(magma_int_t m, magma_int_t n, double **dA_array, magma_int_t ldda,
+                                       magma_int_t *info_array, magma_int_t batchCount, magma_queue_t queue)
+{
+    magma_int_t arginfo = 0;
+    if (m < 0) arginfo = -1;
+    else if (n < 0) arginfo = -2;
+    else if (ldda < imax(1, m)) arginfo = -4;
+    if (arginfo != 0) {
+        magma_xerbla(__func__, -arginfo);
+        return arginfo;
+    }
+    if (batchCount <= 0) return 0;
+    cudaStream_t s = queue->stream;
+    cudaMemsetAsync(info_array, 0, sizeof(int) * (size_t)batchCount, s);  // src/zgetrf_nopiv_batched.cpp:85
+    if (m == 0 || n == 0) return 0;
+    if (m > 512) {
+        magma_xerbla(__func__, -MAGMA_ERR_NOT_SUPPORTED);
+        return MAGMA_ERR_NOT_SUPPORTED;
+    }
+    const Dims d = uniform_dims(m, n, ldda);
+    for (long off = 0; off < batchCount; off += MAX_CHUNK) {
+        const long cnt = std::min<long>(MAX_CHUNK, batchCount - off);
+        const size_t rec_bytes = (lu_blocked_workspace_bytes(cnt) + 255) & ~(size_t)255;
+        const size_t perm_bytes = lu_blocked_perm_bytes(cnt, m, n, true);
+        void *ws = queue_dscratch(queue, rec_bytes + perm_bytes);
+        if (!ws) {
+            magma_xerbla(__func__, -MAGMA_ERR_DEVICE_ALLOC);
+            return MAGMA_ERR_DEVICE_ALLOC;
+        }
+        const magma_int_t rc = lu_blocked_launch(d, m, n, dA_array + off, nullptr, info_array + off, cnt, nullptr, ws, s,
+                                                 (char *)ws + rec_bytes, 1);
+        if (rc != 0) {
+            magma_xerbla(__func__, -rc);
+            return rc;
+        }
+    }
+    return 0;
+}
+
+magma_int_t magma_dgetrs_nopiv_batched(magma_trans_t trans, magma_int_t n, magma_int_t nrhs, double **dA_array,
+                                       magma_int_t ldda, double **dB_array, magma_int_t lddb, magma_int_t *info_array,
+                                       magma_int_t batchCount, magma_queue_t queue)
+{
+    (void)info_array;  // not written by the reference either (src/zgetrs_nopiv_batched.cpp)
+    magma_int_t info = 0;
+    if (trans != MagmaNoTrans && trans != MagmaTrans && trans != MagmaConjTrans) info = -1;
+    else if (n < 0) info = -2;
+    else if (nrhs < 0) info = -3;
+    else if (ldda < imax(1, n)) info = -5;
+    else if (lddb < imax(1, n)) info = -8;
+    if (info != 0) {
+        magma_xerbla(__func__, -info);
+        return info;
+    }
+    if (n == 0 || nrhs == 0 || batchCount <= 0) return 0;
+    for (long off = 0; off < batchCount; off += MAX_CHUNK) {
+        const long cnt = std::min<long>(MAX_CHUNK, batchCount - off);
+        const magma_int_t rc = getrs_launch(trans, n, nrhs, dA_array + off, ldda, nullptr, dB_array + off, lddb, cnt,
+                                            queue->stream);
+        if (rc != 0) {
+            magma_xerbla(__func__, -rc);
+            return rc;
+        }
+    }
+    return 0;
+}
+
+magma_int_t magma_dgesv_nopiv_batched(magma_int_t n, magma_int_t nrhs, double **dA_array, magma_int_t ldda,
+                                      double **dB_array, magma_int_t lddb, magma_int_t *info_array,
+                                      magma_int_t batchCount, magma_queue_t queue)
+{
+    magma_int_t info = 0;
+    if (n < 0) info = -1;
+    else if (nrhs < 0) info = -2;
+    else if (ldda < imax(1, n)) info = -4;
+    else if (lddb < imax(1, n)) info = -6;
+    if (info != 0) {
+        magma_xerbla(__func__, -info);
+        return info;
+    }
+    if (n == 0 || nrhs == 0) return 0;
+    info = magma_dgetrf_nopiv_batched(n, n, dA_array, ldda, info_array, batchCount, queue);
+    if (info != MAGMA_SUCCESS) return info;
+    return magma_dgetrs_nopiv_batched(MagmaNoTrans, n, nrhs, dA_array, ldda, dB_array, lddb, info_array, batchCount, queue);
+}
+
 // inv(A_b) from the factors, out of place.   src/zgetri_outofplace_batched.cpp:81-141
 // The reference forms U^-1 L^-1 I and then applies the column interchanges in reverse; column j of that product is
 // U^-1 L^-1 e_pi(j), i.e. exactly the solve A X = I with the interchanges applied to the identity first: one

@@ -97,10 +97,10 @@ magma_int_t lu_mid_launch(const Dims &d, int max_m, int max_n, double **dA, int 
 // `workspace` must hold lu_blocked_workspace_bytes(batch) bytes (one 512-byte pivot record per matrix).
 // `perm_workspace` (lu_blocked_perm_bytes, may be null): enables the left-looking driver for max_m <= 512.
 size_t lu_blocked_workspace_bytes(long batch);
-size_t lu_blocked_perm_bytes(long batch, int max_m, int max_n);
+size_t lu_blocked_perm_bytes(long batch, int max_m, int max_n, bool any_width = false);
 magma_int_t lu_blocked_launch(const Dims &d, int max_m, int max_n, double **dA, int **dipiv,
                               int *dinfo, long batch, const int *index_list, void *workspace,
-                              cudaStream_t s, void *perm_workspace = nullptr);
+                              cudaStream_t s, void *perm_workspace = nullptr, int nopiv = 0);
 
 // getrs.cu
 magma_int_t getrs_launch(int trans, int n, int nrhs, double **dA, int ldda, int **dipiv,

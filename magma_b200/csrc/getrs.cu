@@ -125,7 +125,7 @@ __device__ void build_perm(int n, const int *__restrict__ ipiv, int *perm, int *
 {
     for (int i = threadIdx.x; i < n; i += SOLVE_THREADS) {
         perm[i] = i;
-        sipiv[i] = ipiv[i] - 1;
+        sipiv[i] = ipiv ? ipiv[i] - 1 : i;  // null: no interchanges (nopiv solves)
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -160,7 +160,7 @@ getrs_kernel(int trans, int n, int nrhs, int tr_max, double **__restrict__ dA, i
     const double *__restrict__ A = dA[b];
     double *__restrict__ B = dB[b] + (size_t)c0 * lddb;
 
-    build_perm(n, dipiv[b], perm, sipiv);
+    build_perm(n, dipiv ? dipiv[b] : nullptr, perm, sipiv);
     if (trans == MagmaNoTrans) {
         for (int idx = threadIdx.x; idx < n * tr; idx += SOLVE_THREADS) {
             const int i = idx % n, c = idx / n;
@@ -232,7 +232,7 @@ __device__ __forceinline__ void stage_diag(double *Ts, const double *__restrict_
 // tracing every position backwards through the interchanges (n independent traces, no serial pass)
 __device__ void build_perm_par(int n, const int *__restrict__ ipiv, int *perm, int *sipiv)
 {
-    for (int i = threadIdx.x; i < n; i += SOLVE_THREADS) sipiv[i] = ipiv[i] - 1;
+    for (int i = threadIdx.x; i < n; i += SOLVE_THREADS) sipiv[i] = ipiv ? ipiv[i] - 1 : i;
     __syncthreads();
     for (int i0 = threadIdx.x; i0 < n; i0 += 2 * SOLVE_THREADS) {
         int c0 = i0, c1 = i0 + SOLVE_THREADS;
@@ -386,7 +386,7 @@ getrs_dmma_kernel(int n, int nrhs, double **__restrict__ dA, int ldda, int **__r
     const int nblk = (n + 31) / 32;
 
     stage_diag(Ts, A, ld, n, 0);
-    build_perm_par(n, dipiv[b], perm, sipiv);
+    build_perm_par(n, dipiv ? dipiv[b] : nullptr, perm, sipiv);
 
     // right-hand sides -> accumulator fragments, interchanges applied on the way in
     double acc[RT][2][2];

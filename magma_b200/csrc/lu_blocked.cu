@@ -43,8 +43,11 @@ template <int R, int W, int MAXT = 512, int MINB = 1>
 __global__ void __launch_bounds__(MAXT, MINB)
 panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__restrict__ dinfo,
              PivRec *__restrict__ recs, int j, long batch, const int *__restrict__ index_list,
-             unsigned short *__restrict__ sinv = nullptr, int sinv_rows = 0, int sinv_blocks = 0)
+             unsigned short *__restrict__ sinv = nullptr, int sinv_rows = 0, int sinv_blocks = 0, int nopiv = 0)
 {
+    // nopiv (R == 1 only): the diagonal element is the pivot whatever its size (magma_dgetrf_nopiv_batched,
+    // magmablas/zgetf2_nopiv_kernels.cu:22-72); a zero diagonal sets info and leaves its column unscaled, the
+    // rank-1 update still runs (LAPACK's dgetf2 convention; the reference stops factoring at that point).
     // sinv (left-looking driver): sinv[panel][p] = position BEFORE this panel of the row that is at position p
     // after it (absolute rows, entries >= j only)
     __shared__ unsigned long long cbits[2][32];
@@ -118,7 +121,7 @@ panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__
                 int ep = (lane < nw) ? cpos[i & 1][lane] : NOPOS;
                 warp_argmax(eb, ep, wb, wp);
             }
-            const int ppos = wp;  // panel-relative position of the pivot row (>= i)
+            const int ppos = nopiv ? i : wp;  // panel-relative position of the pivot row (>= i)
             if (tid == 0) sipiv[i] = ppos;
             if (lp == ppos) {
                 // this thread owns the pivot row (its local winner): publish row and reciprocal
@@ -139,8 +142,9 @@ panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__
             }
             __syncthreads();
             const double piv = prow[i & 1][i];
-            if (piv != 0.0) {
-                const double r = prow[i & 1][W];
+            if (piv == 0.0 && info == 0) info = i + 1;
+            if (piv != 0.0 || nopiv) {
+                const double r = (piv != 0.0) ? prow[i & 1][W] : 1.0;
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
                     if (pos[k] > i && pos[k] != NOPOS) {
@@ -151,8 +155,6 @@ panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__
                             if (c > i) a[k][c] = fma(-l, prow[i & 1][c], a[k][c]);
                     }
                 }
-            } else if (info == 0) {
-                info = i + 1;
             }
         }
     }
@@ -176,7 +178,7 @@ panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__
             }
         }
     }
-    if (tid < jb) dipiv[b][j + tid] = j + sipiv[tid] + 1;
+    if (!nopiv && tid < jb) dipiv[b][j + tid] = j + sipiv[tid] + 1;
     __syncthreads();
     if (tid == 0) {
         rec.n_down = s_ndown;
@@ -1487,22 +1489,22 @@ magma_int_t launch_gemm_dmma(const Dims &d, double **dA, int k0, int rs, int cs,
 // an SM fills it only with other panels.
 inline void launch_panel32(const Dims &d, double **dA, int **dipiv, int *dinfo, PivRec *recs, int j, int T, long batch,
                            const int *il, cudaStream_t s, unsigned short *sinv = nullptr, int sinv_rows = 0,
-                           int sinv_blocks = 0)
+                           int sinv_blocks = 0, int nopiv = 0)
 {
     if (T <= 64)
-        panel_kernel<1, 32, 64, 12><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+        panel_kernel<1, 32, 64, 12><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks, nopiv);
     else if (T <= 96)
-        panel_kernel<1, 32, 96, 8><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+        panel_kernel<1, 32, 96, 8><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks, nopiv);
     else if (T <= 128)
-        panel_kernel<1, 32, 128, 6><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+        panel_kernel<1, 32, 128, 6><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks, nopiv);
     else if (T <= 192)
-        panel_kernel<1, 32, 192, 4><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+        panel_kernel<1, 32, 192, 4><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks, nopiv);
     else if (T <= 256)
-        panel_kernel<1, 32, 256, 3><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+        panel_kernel<1, 32, 256, 3><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks, nopiv);
     else if (T <= 384)
-        panel_kernel<1, 32, 384, 2><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+        panel_kernel<1, 32, 384, 2><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks, nopiv);
     else
-        panel_kernel<1, 32><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks);
+        panel_kernel<1, 32><<<(unsigned)batch, T, 0, s>>>(d, dA, dipiv, dinfo, recs, j, batch, il, sinv, sinv_rows, sinv_blocks, nopiv);
     count_launch();
 }
 
@@ -1630,11 +1632,11 @@ size_t lu_blocked_workspace_bytes(long batch) { return sizeof(PivRec) * (size_t)
 
 // Step-permutation records of the left-looking driver: ceil(min(m,n)/32) arrays of roundup(m,32) 16-bit rows
 // per matrix; 0 when the shape is outside that driver (more than 512 rows, or a single panel).
-size_t lu_blocked_perm_bytes(long batch, int max_m, int max_n)
+size_t lu_blocked_perm_bytes(long batch, int max_m, int max_n, bool any_width)
 {
     const int mn = max_m < max_n ? max_m : max_n;
     // every shape of at most 512 rows (tier 6 keeps the right-looking flow)
-    if (batch <= 0 || max_n <= 32 || max_m > 512) return 0;
+    if (batch <= 0 || (max_n <= 32 && !any_width) || max_m > 512) return 0;
     const size_t rows = (size_t)((max_m + 31) / 32) * 32, blocks = (size_t)(mn + 31) / 32;
     return sizeof(unsigned short) * rows * blocks * (size_t)batch;
 }
@@ -1644,7 +1646,7 @@ namespace {
 // Left-looking driver (max_m <= 512): per 32-column slab one update kernel (everything to its left, once)
 // and one panel kernel; the interchanges of the L columns in one pass at the end.
 magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo, PivRec *recs,
-                             unsigned short *sinv, long batch, const int *il, cudaStream_t s)
+                             unsigned short *sinv, long batch, const int *il, cudaStream_t s, int nopiv)
 {
     const int max_mn = max_m < max_n ? max_m : max_n;
     const int sinv_rows = ((max_m + 31) / 32) * 32, sinv_blocks = (max_mn + 31) / 32;
@@ -1661,7 +1663,7 @@ magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, i
         const int j = 32 * J;
         if (j < max_mn) {
             const int T = ((max_m - j + 31) / 32) * 32;
-            launch_panel32(d, dA, dipiv, dinfo, recs, j, T, batch, il, s, sinv, sinv_rows, sinv_blocks);
+            launch_panel32(d, dA, dipiv, dinfo, recs, j, T, batch, il, s, sinv, sinv_rows, sinv_blocks, nopiv);
             MB200_CHECK_LAUNCH("panel_kernel");
             // a last, narrower panel with columns to its right in the same slab (wide matrices). Variable sizes:
             // any panel may be some matrix's last one, the kernel sorts that out per matrix.
@@ -1669,7 +1671,7 @@ magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, i
             if (partial_here && (rc = left(J, 1)) != 0) return rc;
         }
     }
-    if (max_mn > 32) {
+    if (max_mn > 32 && !nopiv) {  // (no interchanges to apply without pivoting)
         const int blocks = (max_mn - 1) / 32;  // column blocks that have a later panel
         const int T = ((max_m - 32 + 31) / 32) * 32;
         const size_t smem = sizeof(unsigned short) * (size_t)sinv_rows * (size_t)(sinv_blocks - 1);
@@ -1685,16 +1687,22 @@ magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, i
 }  // namespace
 
 magma_int_t lu_blocked_launch(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo,
-                              long batch, const int *index_list, void *workspace, cudaStream_t s, void *perm_workspace)
+                              long batch, const int *index_list, void *workspace, cudaStream_t s, void *perm_workspace,
+                              int nopiv)
 {
     if (batch <= 0) return 0;
+    if (nopiv) {  // no-pivoting LU: the left-looking driver only (register panels of at most 512 rows)
+        if (!perm_workspace || max_m > 512) return MAGMA_ERR_NOT_SUPPORTED;
+        return run_left_looking(d, max_m, max_n, dA, nullptr, dinfo, reinterpret_cast<PivRec *>(workspace),
+                                reinterpret_cast<unsigned short *>(perm_workspace), batch, index_list, s, 1);
+    }
     PivRec *recs = reinterpret_cast<PivRec *>(workspace);
     const int max_mn = max_m < max_n ? max_m : max_n;  // upper bound of min(m_b, n_b)
     // tiers 4 (DFMA only), 5 (no pairing), 6 (right-looking) keep the right-looking flow for A/B runs
     if (perm_workspace && max_n > 32 && max_m <= 512 && g_tier != 4 && g_tier != 5 &&
         g_tier != 6)
         return run_left_looking(d, max_m, max_n, dA, dipiv, dinfo, recs, reinterpret_cast<unsigned short *>(perm_workspace),
-                                batch, index_list, s);
+                                batch, index_list, s, 0);
     const bool defer_left = (max_m <= 512);             // every step is 32 wide
     int pair_end_block = 0;                              // column blocks < this were factored in 64-wide pairs
     int j = 0;

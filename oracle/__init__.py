@@ -59,6 +59,7 @@ def lib():
         L.oracle_dgesv.argtypes = [_i, _i, _pd, _i, _pi, _pd, _i]
         L.oracle_dgesv.restype = _i
         L.oracle_dgetrf_batched.argtypes = [_i, _i, _pd, _i, _l, _pi, _l, _pi, _l]
+        L.oracle_dgetrf_nopiv_batched.argtypes = [_i, _i, _pd, _i, _l, _pi, _l]
         L.oracle_dgetrs_batched.argtypes = [_i, _i, _i, _pd, _i, _l, _pi, _l, _pd, _i, _l, _l]
         L.oracle_dgesv_batched.argtypes = [_i, _i, _pd, _i, _l, _pi, _l, _pd, _i, _l, _pi, _l]
         L.oracle_dgetrf_vbatched.argtypes = [_pi, _pi, _pd, _pi, _pl, _pi, _pl, _pi, _l]
@@ -162,6 +163,21 @@ def gesv_batched(A: np.ndarray, B: np.ndarray, n: int):
     lib().oracle_dgesv_batched(n, nrhs, A.reshape(-1), lda, A.shape[1] * lda, ipiv.reshape(-1), n,
                                B.reshape(-1), ldb, nrhs * ldb, info, batch)
     return ipiv, info
+
+
+def getrf_nopiv_batched(A: np.ndarray, m: int) -> np.ndarray:
+    """In-place LU without pivoting of A[batch, n, ld] (m rows used); returns info (src/zgetrf_nopiv_batched.cpp:75)."""
+    batch, n, ld = A.shape
+    info = np.zeros(batch, dtype=np.int32)
+    lib().oracle_dgetrf_nopiv_batched(m, n, A.reshape(-1), ld, n * ld, info, batch)
+    return info
+
+
+def getrs_nopiv_batched(trans: int, LU: np.ndarray, B: np.ndarray, n: int):
+    """Solve from the no-pivoting factors: oracle_dgetrs with the identity interchanges (src/zgetrs_nopiv_batched.cpp)."""
+    batch = LU.shape[0]
+    ident = np.ascontiguousarray(np.broadcast_to(np.arange(1, n + 1, dtype=np.int32), (batch, n)))
+    getrs_batched(trans, LU, ident, B, n)
 
 
 def getri_outofplace_batched(LU: np.ndarray, ipiv: np.ndarray, n: int) -> np.ndarray:

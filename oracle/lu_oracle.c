@@ -121,6 +121,41 @@ int oracle_dgetf2(int m, int n, double *A, int lda, int *ipiv)
     return info;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * LU without pivoting: magma_dgetrf_nopiv_batched (src/zgetrf_nopiv_batched.cpp:75-170; panel arithmetic
+ * magmablas/zgetf2_nopiv_kernels.cu:22-72: reciprocal of the diagonal, scale, rank-1 update). info = first i with
+ * A(i,i) == 0 at its turn (1-based). At a zero diagonal the column is left unscaled ("reg = 1", :53) and the
+ * update still runs; the reference then abandons the rest of the matrix (:32-34), this restatement -- like the
+ * CUDA path it checks -- completes the factorisation the way LAPACK's dgetf2 would.
+ * ------------------------------------------------------------------------------------------ */
+int oracle_dgetf2_nopiv(int m, int n, double *A, int lda)
+{
+    int info = 0;
+    int mn = m < n ? m : n;
+    for (int k = 0; k < mn; ++k) {
+        double *ck = A + (size_t)k * lda;
+        double r = 1.0;
+        if (ck[k] == 0.0) {
+            if (info == 0) info = k + 1;
+        } else {
+            r = 1.0 / ck[k];
+        }
+        for (int i = k + 1; i < m; ++i) ck[i] *= r;
+        for (int j = k + 1; j < n; ++j) {
+            double *cj = A + (size_t)j * lda;
+            double u = cj[k];
+            for (int i = k + 1; i < m; ++i) cj[i] = fma(-ck[i], u, cj[i]);
+        }
+    }
+    return info;
+}
+
+void oracle_dgetrf_nopiv_batched(int m, int n, double *A, int lda, long strideA, int *info, long batch)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long b = 0; b < batch; ++b) info[b] = oracle_dgetf2_nopiv(m, n, A + b * strideA, lda);
+}
+
 /* LAPACK dlaswp semantics on B (n rows touched by ipiv[0..k-1]), forward or backward. */
 static void apply_pivots(int k, int nrhs, double *B, int ldb, const int *ipiv, int forward)
 {

@@ -332,6 +332,85 @@ def test_getri_argument_errors(gpu_queue):
     assert mb.magma_dgetri_outofplace_batched(0, None, 1, None, None, 1, None, 1, gpu_queue) == 0
 
 
+def _dominant_batch(batch, m, n, seed=3):
+    rng = np.random.default_rng(seed)
+    A = rng.random((batch, n, m)) - 0.5
+    for k in range(min(m, n)):
+        A[:, k, k] += float(max(m, n))
+    return A
+
+
+@pytest.mark.parametrize("m,n,batch", [(1, 1, 5), (5, 5, 9), (16, 16, 33), (32, 32, 9), (20, 9, 7), (9, 20, 7), (33, 33, 6),
+                                       (64, 64, 5), (100, 100, 4), (128, 128, 3), (200, 200, 3), (300, 70, 3), (70, 300, 3),
+                                       (512, 512, 2), (257, 300, 2)])
+def test_getrf_nopiv(gpu_queue, m, n, batch):
+    """magma_dgetrf_nopiv_batched: bit-identical to oracle_dgetf2_nopiv."""
+    A0 = _dominant_batch(batch, m, n)
+    A0[0] = oracle.random_batch(1, m, n)[0][0]  # one general matrix: no pivoting is still well defined, just less stable
+    db = mb.DeviceBatch(batch, m, n, queue=gpu_queue)
+    db.upload(A0)
+    db.info.fill_(-3)
+    assert mb.magma_dgetrf_nopiv_batched(m, n, db.dA_array, db.ldda, db.info, batch, gpu_queue) == 0
+    LU, _, info = db.download()
+    ref = A0.copy()
+    info_ref = oracle.getrf_nopiv_batched(ref, m)
+    assert np.array_equal(info, info_ref)
+    assert np.array_equal(LU, ref), f"max diff {np.max(np.abs(LU - ref))}"
+
+
+def test_getrf_nopiv_zero_diagonal(gpu_queue):
+    n, batch = 40, 4
+    A0 = _dominant_batch(batch, n, n)
+    A0[1, 7, :] = 0.0      # zero column: A(7,7) is zero at its turn
+    A0[2, 0, 0] = 0.0      # zero first pivot
+    A0[3, 35, :] = 0.0     # zero column in the second panel
+    db = mb.DeviceBatch(batch, n, n, queue=gpu_queue)
+    db.upload(A0)
+    assert mb.magma_dgetrf_nopiv_batched(n, n, db.dA_array, db.ldda, db.info, batch, gpu_queue) == 0
+    LU, _, info = db.download()
+    ref = A0.copy()
+    info_ref = oracle.getrf_nopiv_batched(ref, n)
+    assert list(info_ref) == [0, 8, 1, 36]
+    assert np.array_equal(info, info_ref)
+    assert np.array_equal(LU, ref, equal_nan=True)
+
+
+@pytest.mark.parametrize("n,nrhs", [(7, 2), (32, 1), (75, 4), (160, 16)])
+def test_gesv_and_getrs_nopiv(gpu_queue, n, nrhs):
+    batch = 6
+    A0 = _dominant_batch(batch, n, n)
+    B0 = np.random.default_rng(9).random((batch, nrhs, n))
+    db = mb.DeviceBatch(batch, n, n, nrhs=nrhs, queue=gpu_queue)
+    db.upload(A0, B0)
+    assert mb.magma_dgesv_nopiv_batched(n, nrhs, db.dA_array, db.ldda, db.dB_array, db.lddb, db.info, batch,
+                                        gpu_queue) == 0
+    LU, _, info, X = db.download()
+    ref = A0.copy()
+    assert not oracle.getrf_nopiv_batched(ref, n).any() and not info.any()
+    assert np.array_equal(LU, ref)
+    Xr = B0.copy()
+    oracle.getrs_nopiv_batched(mb.MagmaNoTrans, ref, Xr, n)
+    assert np.array_equal(X, Xr)
+    assert oracle.solve_residual(mb.MagmaNoTrans, A0, X, B0, n) < oracle.TOL
+    # transposed solve from the same factors
+    db.B.copy_(db.torch.from_numpy(B0))
+    assert mb.magma_dgetrs_nopiv_batched(mb.MagmaTrans, n, nrhs, db.dA_array, db.ldda, db.dB_array, db.lddb, db.info,
+                                         batch, gpu_queue) == 0
+    Xt = db.download()[3]
+    Xtr = B0.copy()
+    oracle.getrs_nopiv_batched(mb.MagmaTrans, ref, Xtr, n)
+    assert np.array_equal(Xt, Xtr)
+
+
+def test_nopiv_argument_errors(gpu_queue):
+    assert mb.magma_dgetrf_nopiv_batched(-1, 4, None, 4, None, 1, gpu_queue) == -1
+    assert mb.magma_dgetrf_nopiv_batched(4, -1, None, 4, None, 1, gpu_queue) == -2
+    assert mb.magma_dgetrf_nopiv_batched(4, 4, None, 3, None, 1, gpu_queue) == -4
+    assert mb.magma_dgetrs_nopiv_batched(5, 4, 1, None, 4, None, 4, None, 1, gpu_queue) == -1
+    assert mb.magma_dgetrs_nopiv_batched(mb.MagmaNoTrans, 4, 1, None, 3, None, 4, None, 1, gpu_queue) == -5
+    assert mb.magma_dgesv_nopiv_batched(4, 1, None, 4, None, 3, None, 1, gpu_queue) == -6
+
+
 # ---- variable-size batch ------------------------------------------------------------------------
 
 def _vbatched_case(q, ms, ns, lds=None, expert=False):

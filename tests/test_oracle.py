@@ -118,6 +118,48 @@ def test_getri_vs_lapack():
             assert r < oracle.TOL
 
 
+def _dominant_batch(batch, m, n, seed=3):
+    """Matrices that need no pivoting: random + a dominant diagonal (stored layout [b][col][row])."""
+    rng = np.random.default_rng(seed)
+    A = rng.random((batch, n, m)) - 0.5
+    for k in range(min(m, n)):
+        A[:, k, k] += float(max(m, n))
+    return A
+
+
+def test_nopiv_oracle_vs_lapack():
+    """oracle.getrf_nopiv_batched: on diagonally dominant matrices partial pivoting never
+    interchanges, so host LAPACK's dgetrf must give identity pivots and (to rounding) the same factors; the solve
+    from those factors passes the testers' residual check."""
+    L = oracle.lapack()
+    for m, n, batch in ((1, 1, 3), (7, 7, 9), (40, 40, 6), (33, 20, 4), (20, 33, 4), (130, 130, 2)):
+        A0 = _dominant_batch(batch, m, n)
+        LU = A0.copy()
+        info = oracle.getrf_nopiv_batched(LU, m)
+        assert not info.any()
+        ref = A0.copy()
+        mn = min(m, n)
+        ipiv = np.zeros((batch, mn), dtype=np.int32)
+        inf2 = np.zeros(batch, dtype=np.int32)
+        L.lapack_dgetrf_loop(m, n, ref.reshape(-1), m, n * m, ipiv.reshape(-1), mn, inf2, batch)
+        assert np.array_equal(ipiv, np.broadcast_to(np.arange(1, mn + 1, dtype=np.int32), (batch, mn)))
+        assert np.allclose(LU, ref, rtol=1e-12, atol=1e-13)
+    n, nrhs, batch = 40, 3, 5
+    A0 = _dominant_batch(batch, n, n)
+    B0 = np.random.default_rng(4).random((batch, nrhs, n))
+    LU = A0.copy()
+    oracle.getrf_nopiv_batched(LU, n)
+    for trans in (oracle.MagmaNoTrans, oracle.MagmaTrans):
+        X = B0.copy()
+        oracle.getrs_nopiv_batched(trans, LU, X, n)
+        assert oracle.solve_residual(trans, A0, X, B0, n) < oracle.TOL
+    # zero diagonal: info = first such column, factorisation completed with the column unscaled
+    Z = _dominant_batch(1, 6, 6)
+    Z[0, 2, :] = 0.0   # column 2 of the matrix entirely zero -> A(2,2) stays 0 after two steps
+    info = oracle.getrf_nopiv_batched(Z, 6)
+    assert info[0] == 3 and np.isfinite(Z).all()
+
+
 def test_singular_and_tie_semantics():
     # zero matrix: info = 1, ipiv = identity, nothing scaled (smallsq_noshfl.cu:90-91,106)
     Z = np.zeros((1, 5, 5))

@@ -451,6 +451,27 @@ def run_sweep(mb, torch, np, q, local, rank, world, barrier, max_over_ranks, sum
 
     getri("F1 dgetri_outofplace_batched n=64 batch=100000", 64, 100_000)
 
+    # F2: LU without pivoting, n = 128 (diagonally dominant inputs: dlarnv + n on the diagonal)
+    def nopiv(name, n, batch, reps=5):
+        db = mb.DeviceBatch(batch, n, n, device=local, queue=q)
+        seed = np.array([41, rank, 0, 1], dtype=np.int32)
+        mb.dlarnv_uniform(seed, batch * n * n, db.A, q)
+        q.sync()
+        db.A.diagonal(dim1=1, dim2=2).add_(float(n))
+        A0 = db.A.clone()
+        fn = lambda: mb.magma_dgetrf_nopiv_batched(n, n, db.dA_array, db.ldda, db.info, batch, q)  # noqa: E731
+        med, best = timed(fn, lambda: db.A.copy_(A0), reps)
+        gf = flops_getrf(n, n) * batch * world / (med * 1e-3) / 1e9
+        roof = min(flops_getrf(n, n) / (16.0 * n * n) * hbm_peak, fp64_peak)
+        out.append({"config": name, "n": n, "batch_per_gpu": batch, "ms": med, "ms_best": best, "gflops": gf,
+                    "gflops_per_gpu": gf / world, "roofline_gflops": roof, "frac_of_roofline": gf / world / roof,
+                    "alg_GBs_per_gpu": 16.0 * n * n * batch / (med * 1e-3) / 1e9,
+                    "info_max": int(db.info.abs().max().item())})
+        del db, A0
+        torch.cuda.empty_cache()
+
+    nopiv("F2 dgetrf_nopiv_batched n=128 batch=50000", 128, 50_000)
+
     # C4: vbatched, sizes 16 + (lcg mod 497), square, ldda = n
     batch = 20_000
     x = 1234 + rank

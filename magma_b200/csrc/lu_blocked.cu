@@ -108,20 +108,20 @@ panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__
                 if (lk == k) cv = a[k][i];
             const double rinv = 1.0 / cv;
 
-            unsigned long long wb;
-            int wp;
-            warp_argmax(lb, lp, wb, wp);
-            if (lane == 0) {
-                cbits[i & 1][wid] = wb;
-                cpos[i & 1][wid] = wp;
-            }
-            __syncthreads();
-            {
+            int wp = i;  // nopiv: the diagonal
+            if (!nopiv) {  // kernel-uniform
+                unsigned long long wb;
+                warp_argmax(lb, lp, wb, wp);
+                if (lane == 0) {
+                    cbits[i & 1][wid] = wb;
+                    cpos[i & 1][wid] = wp;
+                }
+                __syncthreads();
                 unsigned long long eb = (lane < nw) ? cbits[i & 1][lane] : 0ull;
                 int ep = (lane < nw) ? cpos[i & 1][lane] : NOPOS;
                 warp_argmax(eb, ep, wb, wp);
             }
-            const int ppos = nopiv ? i : wp;  // panel-relative position of the pivot row (>= i)
+            const int ppos = wp;  // panel-relative position of the pivot row (>= i)
             if (tid == 0) sipiv[i] = ppos;
             if (lp == ppos) {
                 // this thread owns the pivot row (its local winner): publish row and reciprocal

@@ -110,16 +110,20 @@ panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__
 
             int wp = i;  // nopiv: the diagonal
             if (!nopiv) {  // kernel-uniform
-                unsigned long long wb;
-                warp_argmax(lb, lp, wb, wp);
-                if (lane == 0) {
-                    cbits[i & 1][wid] = wb;
-                    cpos[i & 1][wid] = wp;
+                // the winning lane hands over its own candidate (no shuffle of the winner's values to every lane)
+                const int wl = warp_argmax_lane(lb, lp);
+                if (nw == 1) {  // single-warp panel: decided
+                    wp = __shfl_sync(0xffffffffu, lp, wl);
+                } else {
+                    if (lane == wl) {
+                        cbits[i & 1][wid] = lb;
+                        cpos[i & 1][wid] = lp;
+                    }
+                    __syncthreads();
+                    const unsigned long long eb = (lane < nw) ? cbits[i & 1][lane] : 0ull;
+                    const int ep = (lane < nw) ? cpos[i & 1][lane] : NOPOS;
+                    wp = __shfl_sync(0xffffffffu, ep, warp_argmax_lane(eb, ep));
                 }
-                __syncthreads();
-                unsigned long long eb = (lane < nw) ? cbits[i & 1][lane] : 0ull;
-                int ep = (lane < nw) ? cpos[i & 1][lane] : NOPOS;
-                warp_argmax(eb, ep, wb, wp);
             }
             const int ppos = wp;  // panel-relative position of the pivot row (>= i)
             if (tid == 0) sipiv[i] = ppos;

@@ -1215,24 +1215,56 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
     }
     __syncthreads();
     stage_lkk(kfirst);
-#pragma unroll
-    for (int pch = 0; pch < ahead; ++pch) issue(pch);
 
     // ---- the slab, rows in current order ---------------------------------------------------------------------
+    // Copied with contiguous 16-byte cp.asyncs (original row order) into the ring, which the L chunks do not need
+    // yet, and picked up through src[] from shared memory: the direct gather cost 26 tag requests per 8-byte warp load
+    // and a fifth of the kernel's time on the middle slabs.
+    constexpr int SCOLS = (RING * 8 >= 32) ? 32 : 16;  // slab columns the ring can hold at once
     double acc[4][4][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int row = 8 * (w + NW * a) + g;
-        const bool rok = row < m;
-        const double *src = A + S.src[row] + (size_t)(c0 + 2 * q) * ld;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int col = 8 * c + 2 * q;
-            acc[a][c][0] = (rok && col >= cb && col < nc) ? src[(size_t)(8 * c) * ld] : 0.0;
-            acc[a][c][1] = (rok && col + 1 >= cb && col + 1 < nc) ? src[(size_t)(8 * c + 1) * ld] : 0.0;
+    for (int p0 = 0; p0 < 32; p0 += SCOLS) {
+        if (vec_ok) {
+            const int npairs = (m + 1) >> 1;
+            const unsigned magic = 0xFFFFFFFFu / (unsigned)npairs + 1u;
+            for (int u = tid; u < SCOLS * npairs; u += T) {
+                const int cc = npairs > 1 ? (int)__umulhi((unsigned)u, magic) : u, r = 2 * (u - cc * npairs);
+                const int col = p0 + cc;
+                const bool ok = (col >= cb && col < nc);
+                const int bytes = ok ? ((r + 1 < m) ? 16 : 8) : 0;
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(S.ring + cc * LDR + r);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa),
+                             "l"(ok ? A + r + (size_t)(c0 + col) * ld : A), "r"(bytes)
+                             : "memory");
+            }
+        } else {
+            const unsigned magic = 0xFFFFFFFFu / (unsigned)m + 1u;
+            for (int u = tid; u < SCOLS * m; u += T) {
+                const int cc = m > 1 ? (int)__umulhi((unsigned)u, magic) : u, r = u - cc * m;
+                const int col = p0 + cc;
+                const bool ok = (col >= cb && col < nc);
+                cp_async8(S.ring + cc * LDR + r, ok ? A + r + (size_t)(c0 + col) * ld : A, ok);
+            }
         }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int row = 8 * (w + NW * a) + g;
+            const bool rok = row < m;
+            const double *sp = S.ring + (rok ? (int)S.src[row] : 0) + (2 * q - p0) * LDR;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (8 * c >= p0 && 8 * c < p0 + SCOLS) {  // static
+                    acc[a][c][0] = rok ? sp[(8 * c) * LDR] : 0.0;
+                    acc[a][c][1] = rok ? sp[(8 * c + 1) * LDR] : 0.0;
+                }
+            }
+        }
+        __syncthreads();  // the ring is free again; every row of these columns is in registers
     }
-    __syncthreads();  // every row is in registers: stores into the slab may begin
+#pragma unroll 1
+    for (int pch = 0; pch < ahead; ++pch) issue(pch);
 
     int nrel = 0;  // chunk consumed next, counted from the first step
 #pragma unroll 1

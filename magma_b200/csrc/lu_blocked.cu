@@ -1361,18 +1361,16 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             const int row = 8 * (w + NW * a) + g;
             roff[a] = (row < m) ? (int)S.rmap[K][row] : 32 * (K + 1);  // rows past m: any row of the chunk
         }
-        auto ring_pass = [&](auto amin_c) {
-            constexpr int AMIN = decltype(amin_c)::value;
-            bool on[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) on[a] = (a >= AMIN) && (8 * (w + NW * a) < m);  // rows past m: predicated
+        auto ring_pass = [&](auto amin_c, auto aend_c) {
+            constexpr int AMIN = decltype(amin_c)::value;   // first active tile slot
+            constexpr int AEND = decltype(aend_c)::value;   // one past the last tile slot that has rows (< m)
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {
                 issue(nrel + ahead);
                 if (ch == 0 && K + 1 < nk) stage_lkk(K + 1);
                 const int slot_r = nrel % RING;
                 ll_mbar_wait(&S.full[slot_r], (unsigned)((nrel / RING) & 1));
-                if (AMIN < 4) {
+                if (AMIN < AEND) {
                     const double *As = S.ring + (size_t)slot_r * 8 * LDR + q * LDR;
 #pragma unroll
                     for (int s2 = 0; s2 < 2; ++s2) {
@@ -1380,12 +1378,10 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
 #pragma unroll
                         for (int c = 0; c < 4; ++c) bf[c] = Un[(8 * ch + 4 * s2 + q) * LL_LDU + 8 * c + g];
 #pragma unroll
-                        for (int a = AMIN; a < 4; ++a) {
-                            if (on[a]) {
-                                const double af = As[4 * s2 * LDR + roff[a]];
+                        for (int a = AMIN; a < AEND; ++a) {
+                            const double af = As[4 * s2 * LDR + roff[a]];
 #pragma unroll
-                                for (int c = 0; c < 4; ++c) dmma_884(acc[a][c][0], acc[a][c][1], af, bf[c]);
-                            }
+                            for (int c = 0; c < 4; ++c) dmma_884(acc[a][c][0], acc[a][c][1], af, bf[c]);
                         }
                     }
                 }
@@ -1397,13 +1393,27 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             // first tile slot a with w + NW a > 4K + 3
             const int need = 4 * K + 4 - w;  // tiles t >= 4K+4  <=>  NW a >= need
             const int amin = need <= 0 ? 0 : (need + NW - 1) / NW;
-            switch (amin) {
-                case 0: ring_pass(std::integral_constant<int, 0>{}); break;
-                case 1: ring_pass(std::integral_constant<int, 1>{}); break;
-                case 2: ring_pass(std::integral_constant<int, 2>{}); break;
-                case 3: ring_pass(std::integral_constant<int, 3>{}); break;
-                default: ring_pass(std::integral_constant<int, 4>{}); break;
+            // tile slots of this warp that hold rows of the matrix: a < aend (a matrix shorter than the CTA's reach,
+            // e.g. 384 rows under 16 warps or any vbatched class member, must not issue DMMAs for the missing tiles:
+            // predicated off they would still occupy the tensor pipe)
+            const int tiles_m = (m + 7) >> 3;
+            const int aend = tiles_m <= w ? 0 : ((tiles_m - w + NW - 1) / NW > 4 ? 4 : (tiles_m - w + NW - 1) / NW);
+            const int a0 = amin < aend ? amin : aend;  // nothing to do: (aend, aend)
+#define MB200_RP(A0, A1) ring_pass(std::integral_constant<int, A0>{}, std::integral_constant<int, A1>{})
+            switch (a0 * 5 + aend) {
+                case 0 * 5 + 4: MB200_RP(0, 4); break;
+                case 1 * 5 + 4: MB200_RP(1, 4); break;
+                case 2 * 5 + 4: MB200_RP(2, 4); break;
+                case 3 * 5 + 4: MB200_RP(3, 4); break;
+                case 0 * 5 + 3: MB200_RP(0, 3); break;
+                case 1 * 5 + 3: MB200_RP(1, 3); break;
+                case 2 * 5 + 3: MB200_RP(2, 3); break;
+                case 0 * 5 + 2: MB200_RP(0, 2); break;
+                case 1 * 5 + 2: MB200_RP(1, 2); break;
+                case 0 * 5 + 1: MB200_RP(0, 1); break;
+                default: MB200_RP(0, 0); break;  // no tile: keep the pipeline protocol running
             }
+#undef MB200_RP
         }
     }
 

@@ -1,20 +1,34 @@
-// Blocked right-looking LU for any m x n: three specialised kernels per 32-column panel step.
+// Blocked LU for any m x n, two drivers over the same register panel kernel.
 //
 // Replaces the reference's host recursion (src/zgetrf_batched.cpp:149-203 ->
 // src/zgetrf_panel_batched.cpp:101-196 -> src/zgetf2_batched.cpp:95-287), which issues 42/105/231
 // launches per call at n = 128/256/512: fused panel, setup_pivinfo, adjust_ipiv, 2x laswp,
-// recursive trsm, cublasDgemmBatched (+3 pointer-displacement kernels each). Here a step is
+// recursive trsm, cublasDgemmBatched (+3 pointer-displacement kernels each).
+//
 //   panel_kernel  : one CTA per matrix, panel rows in registers (thread = R rows x W columns),
 //                   CREDUX + shared-memory two-level pivot search, lazy row interchanges; writes
-//                   the factored panel in final row order, ipiv (global indices) and the step's
-//                   net row permutation (which rows land in the top block, which top rows go
-//                   down) into a 512-byte per-matrix record -- the threads know it from their
-//                   final positions, there is no setup_pivinfo / adjust_ipiv pass;
+//                   the factored panel in final row order, ipiv (global indices), the step's
+//                   net row permutation as a 512-byte record (right-looking driver) and as a 16-bit
+//                   position table (left-looking driver) -- the threads know both from their
+//                   final positions, there is no setup_pivinfo / adjust_ipiv pass. Instantiated
+//                   per panel height with an 80-register budget (2..12 CTAs per SM).
+//
+// LEFT-LOOKING driver (at most 512 rows: the default): per 32-column slab
+//   left_update_kernel<NW> : one CTA owns the slab for its whole history -- reads it once through
+//                   the composed row permutation, keeps it as DMMA accumulator fragments, and for
+//                   every earlier panel solves the block row and subtracts L(:,K) U(K,J) on the
+//                   FP64 tensor pipe; L streams through a CTA-wide cp.async ring handed over by
+//                   mbarriers. No physical interchange touches the trailing matrix.
+//   laswp_left_sinv_kernel : the deferred interchanges of the L columns, one pass at the end.
+//
+// RIGHT-LOOKING driver (more rows, or magma_b200_set_tier(6)): per 64 columns
 //   swap_trsm_kernel : one CTA per (matrix, 64-column tile): applies the permutation to the tile
 //                   (left tiles: interchanges only), and for tiles right of the panel solves the
 //                   W x 64 block row against the unit-lower L11 and stores U12;
-//   gemm_kernel   : C(r,c) = fma(-L21(r,k), U12(k,c), C(r,c)), k increasing, one 128x64 tile per
-//                   CTA (4x8 register tiles, operands staged once in shared memory).
+//   gemm_dmma_kernel / gemm_kernel : C(r,c) = fma(-L21(r,k), U12(k,c), C(r,c)), k increasing, one
+//                   128x64 tile per CTA on the tensor pipe (DFMA fallback: tier 4);
+//   update_strip_kernel, laswp_left_kernel : short trailing strips in shared memory; deferred
+//                   interchanges replayed from ipiv.
 // All arithmetic is in the canonical order of oracle/lu_oracle.c: bit-identical factors.
 #include "lu_common.cuh"
 #include <type_traits>

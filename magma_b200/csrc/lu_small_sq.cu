@@ -369,20 +369,36 @@ lu_sqs_kernel(double *const *__restrict__ dA, int *const *__restrict__ dipiv, in
     double mydinv[R];
     unsigned pos[R];
     int myipiv[R];
+    // A lane starts with the ADJACENT rows 2 sub and 2 sub + 1: one 16-byte load per column brings both, and a
+    // group's eight lanes cover a whole 128-byte column of the matrix per instruction (with rows sub and sub + G a
+    // warp load touched four half-used lines: 4 tag wavefronts per 8-byte instruction, 136 per pass instead of 68).
+    // Which rows a lane starts with is immaterial afterwards: everything below works on positions.
+    // (n = 8 keeps rows sub and sub + G: the 64-register budget of that variant does not survive the extra path.)
+    constexpr bool ADJ = (N == 16);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        pos[r] = (unsigned)(sub + r * G);
+        pos[r] = (unsigned)(ADJ ? 2 * sub + r : sub + r * G);
         myipiv[r] = 0;
         mydinv[r] = 0.0;
         rb[r] = 0.0;
-#pragma unroll
-        for (int j = 0; j < N; ++j) a[r][j] = ldg64(A + (sub + r * G) + (size_t)j * ld);
     }
     double *B = nullptr;
-    if (NRHS) {
-        B = Bcur;
+    if (NRHS) B = Bcur;
+    const bool v128 = ADJ &&
+                      __all_sync(FULL, ((reinterpret_cast<uintptr_t>(A) | (NRHS ? reinterpret_cast<uintptr_t>(Bcur) : (uintptr_t)0)) & 15) == 0) &&
+                      (LDN || (ldda & 1) == 0);
+    if (v128) {  // warp-uniform
 #pragma unroll
-        for (int r = 0; r < R; ++r) rb[r] = ldg64(B + sub + r * G);
+        for (int j = 0; j < N; ++j)
+            asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(a[0][j]), "=d"(a[1][j]) : "l"(A + 2 * sub + (size_t)j * ld));
+        if (NRHS) asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(rb[0]), "=d"(rb[1]) : "l"(B + 2 * sub));
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) a[r][j] = ldg64(A + pos[r] + (size_t)j * ld);
+            if (NRHS) rb[r] = ldg64(B + pos[r]);
+        }
     }
     unsigned zmask = 0;  // bit i set: column i had an exactly zero pivot
 

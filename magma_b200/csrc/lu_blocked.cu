@@ -1472,7 +1472,7 @@ magma_int_t launch_left_update(const Dims &d, double **dA, const unsigned short 
 
 // -------------------------------------------------------------------------------------------
 // Deferred interchanges of the L part when the step permutations are on record (left-looking driver):
-// one CTA per (matrix, column block J, group of 8 columns), thread = row. The source row of every
+// one CTA per (matrix, column block J), thread = row, 8 columns at a time. The source row of every
 // final position comes from walking the recorded permutations back (nk - J - 1 table look-ups in
 // shared memory, all rows in parallel) instead of replaying up to 480 interchanges on one thread;
 // each thread holds its 8 values in registers across ONE barrier (all reads of a column precede all
@@ -1488,9 +1488,8 @@ laswp_left_sinv_kernel(Dims d, double **__restrict__ dA, const unsigned short *_
     unsigned short *tab = reinterpret_cast<unsigned short *>(smem_raw);  // [later panels][sinv_rows]
 
     constexpr int GROUPS = 32 / LSP_COLS;
-    const int grp = blockIdx.x % GROUPS;
-    const int J = (blockIdx.x / GROUPS) % blocks;
-    const long slot = blockIdx.x / (GROUPS * blocks);
+    const int J = blockIdx.x % blocks;
+    const long slot = blockIdx.x / blocks;
     const long b = index_list ? index_list[slot] : slot;
     if (b < 0) return;
     int m, n, ld;
@@ -1512,14 +1511,19 @@ laswp_left_sinv_kernel(Dims d, double **__restrict__ dA, const unsigned short *_
             if (r >= 32 * K) r = tab[(K - J - 1) * sinv_rows + r];
     }
     const bool moved = live && (r != r0 + tid);
-    double *__restrict__ A = dA[b] + (size_t)(32 * J + LSP_COLS * grp) * ld;
-    double v[LSP_COLS];
+    // the block's 32 columns in groups of 8 (one table and one walk per block; groups touch disjoint columns, so
+    // one barrier per group -- all reads of its columns before any write -- is enough)
+#pragma unroll 1
+    for (int grp = 0; grp < GROUPS; ++grp) {
+        double *__restrict__ A = dA[b] + (size_t)(32 * J + LSP_COLS * grp) * ld;
+        double v[LSP_COLS];
 #pragma unroll
-    for (int c = 0; c < LSP_COLS; ++c) v[c] = moved ? A[r + (size_t)c * ld] : 0.0;
-    __syncthreads();
-    if (moved) {
+        for (int c = 0; c < LSP_COLS; ++c) v[c] = moved ? A[r + (size_t)c * ld] : 0.0;
+        __syncthreads();
+        if (moved) {
 #pragma unroll
-        for (int c = 0; c < LSP_COLS; ++c) A[r0 + tid + (size_t)c * ld] = v[c];
+            for (int c = 0; c < LSP_COLS; ++c) A[r0 + tid + (size_t)c * ld] = v[c];
+        }
     }
 }
 
@@ -1735,7 +1739,7 @@ magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, i
         const int blocks = (max_mn - 1) / 32;  // column blocks that have a later panel
         const int T = ((max_m - 32 + 31) / 32) * 32;
         const size_t smem = sizeof(unsigned short) * (size_t)sinv_rows * (size_t)(sinv_blocks - 1);
-        const long grid = (long)blocks * batch * (32 / LSP_COLS);
+        const long grid = (long)blocks * batch;
         if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
         laswp_left_sinv_kernel<<<(unsigned)grid, T, smem, s>>>(d, dA, sinv, sinv_rows, sinv_blocks, blocks, batch, il);
         count_launch();

@@ -268,6 +268,34 @@ magma_int_t magma_dgesv_batched_small(magma_int_t n, magma_int_t nrhs, double **
 void magma_dlaswp_rowserial_batched(magma_int_t n, double **dA_array, magma_int_t lda, magma_int_t k1,
                                     magma_int_t k2, magma_int_t **ipiv_array, magma_int_t batchCount,
                                     magma_queue_t queue);
+/* Panel-level entry points of the reference, kept for source compatibility (include/magma_zbatched.h:829-855).
+ * Each factors the m x n block at (ai, aj) of every matrix: pivots are 1-based RELATIVE to row ai and written at
+ * ipiv_array[b] + ai; a zero pivot at panel step i records gbstep + i + 1 in info_array[b] unless an earlier panel
+ * already recorded one (gbstep == 0 resets it). dpivinfo_array / min_recpnb steer the reference's implementation
+ * and are ignored here; the work runs on the same kernels as magma_dgetrf_batched.
+ *   magma_dgetf2_fused_batched     magmablas/zgetf2_kernels.cu:1005-1058 (n <= 32, gbstep = aj)
+ *   magma_dgetf2_batched           src/zgetf2_batched.cpp:243-287
+ *   magma_dgetrf_recpanel_batched  src/zgetrf_panel_batched.cpp:101-196 */
+magma_int_t magma_dgetf2_fused_batched(magma_int_t m, magma_int_t n, double **dA_array, magma_int_t ai, magma_int_t aj,
+                                       magma_int_t ldda, magma_int_t **dipiv_array, magma_int_t *info_array,
+                                       magma_int_t batchCount, magma_queue_t queue);
+magma_int_t magma_dgetf2_batched(magma_int_t m, magma_int_t n, double **dA_array, magma_int_t ai, magma_int_t aj,
+                                 magma_int_t lda, magma_int_t **ipiv_array, magma_int_t **dpivinfo_array,
+                                 magma_int_t *info_array, magma_int_t gbstep, magma_int_t batchCount, magma_queue_t queue);
+magma_int_t magma_dgetrf_recpanel_batched(magma_int_t m, magma_int_t n, magma_int_t min_recpnb, double **dA_array,
+                                          magma_int_t ai, magma_int_t aj, magma_int_t ldda, magma_int_t **dipiv_array,
+                                          magma_int_t **dpivinfo_array, magma_int_t *info_array, magma_int_t gbstep,
+                                          magma_int_t batchCount, magma_queue_t queue);
+/* Row permutation by a pivinfo table: new[r] = old[pivinfo[r]-1] for the k2-k1 top rows (written to output) and for
+ * the rows they came from (written in place in input).   magmablas/zlaswp_batched.cu:47-87 */
+void magma_dlaswp_rowparallel_batched(magma_int_t n, double **input_array, magma_int_t input_i, magma_int_t input_j,
+                                      magma_int_t ldi, double **output_array, magma_int_t output_i, magma_int_t output_j,
+                                      magma_int_t ldo, magma_int_t k1, magma_int_t k2, magma_int_t **pivinfo_array,
+                                      magma_int_t batchCount, magma_queue_t queue);
+/* x_b <- op(A_b)^-1 x_b in place, increment incb > 0.   magmablas/ztrsv_batched.cu:258-298 */
+void magmablas_dtrsv_batched(magma_uplo_t uplo, magma_trans_t transA, magma_diag_t diag, magma_int_t n, double **dA_array,
+                             magma_int_t ldda, double **dB_array, magma_int_t incb, magma_int_t batchCount,
+                             magma_queue_t queue);
 /* B_b <- alpha * op(A_b)^-1 B_b, side = Left only on this path.   magmablas/ztrsm_batched_core.cpp:299-350 */
 void magmablas_dtrsm_batched(magma_side_t side, magma_uplo_t uplo, magma_trans_t transA, magma_diag_t diag,
                              magma_int_t m, magma_int_t n, double alpha, double **dA_array, magma_int_t ldda,
@@ -328,6 +356,10 @@ int64_t magma_b200_launch_count(void);
  * 4 = blocked tier and getrs on the DFMA kernels only (no tensor pipe), 5 = no 64-wide pairing,
  * 6 = right-looking blocked driver everywhere, 7 = left-looking slab driver up to 512 rows (default: 448). */
 void magma_b200_set_tier(int tier);
+/* Self-test of the inline reciprocal of lu_fused.cu: mismatches against IEEE 1.0/x over n pseudo-random inputs (0 expected). */
+int64_t magma_b200_rcp_selftest(int64_t n, magma_queue_t queue);
+/* Largest max(m,n) routed to the single-launch shared-memory tier (lu_fused.cu), 0..128; 0 disables it (A/B runs). */
+void magma_b200_set_fused_max(int n);
 /* Largest max(m,n) routed to the register-file tier (lu_mid.cu), 32..128; for tuning sweeps. */
 void magma_b200_set_mid_max(int n);
 /* Register tier layout override for tuning sweeps: rows per lane (1 or 2), 0 = tuned default; 3/4 = alternative

@@ -93,6 +93,13 @@ SIGNATURES = {
     "magma_b200_set_tier": (None, [i32]),
     "magma_b200_set_small_rows": (None, [i32]),
     "magma_b200_set_mid_max": (None, [i32]),
+    "magma_b200_set_fused_max": (None, [i32]),
+    "magma_b200_rcp_selftest": (i64, [i64, vp]),
+    "magma_dgetf2_fused_batched": (i32, [i32, i32, vp, i32, i32, i32, vp, vp, i32, vp]),
+    "magma_dgetf2_batched": (i32, [i32, i32, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp]),
+    "magma_dgetrf_recpanel_batched": (i32, [i32, i32, i32, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp]),
+    "magma_dlaswp_rowparallel_batched": (None, [i32, vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "magmablas_dtrsv_batched": (None, [i32, i32, i32, i32, vp, i32, vp, i32, i32, vp]),
     "magmaf_dgetrf_batched_": (None, [vp] * 9),
     "magmaf_dgetrs_batched_": (None, [cstr] + [vp] * 10),
     "magmaf_dgesv_batched_": (None, [vp] * 11),

@@ -29,7 +29,7 @@ __all__ = [
     "magma_dgetrf_nopiv_batched", "magma_dgetrs_nopiv_batched", "magma_dgesv_nopiv_batched",
     "magma_dgesv_batched_small", "magma_dset_pointer", "magma_iset_pointer", "magma_ddisplace_pointers",
     "magma_dlaswp_rowserial_batched", "magmablas_dtrsm_batched", "magma_dgemm_batched_core",
-    "magma_get_dgetrf_batched_nbparam", "dlarnv_uniform", "set_tier", "set_small_rows", "set_mid_max", "launch_count",
+    "magma_get_dgetrf_batched_nbparam", "dlarnv_uniform", "set_tier", "set_small_rows", "set_mid_max", "set_fused_max", "launch_count",
     "fp64_peak_tflops", "hbm_copy_gbs", "DeviceBatch", "dgetrf_batched_host", "dgesv_batched_host",
 ]
 
@@ -215,6 +215,14 @@ def set_tier(tier: int):
 
 def set_small_rows(rows: int):
     _lib.load().magma_b200_set_small_rows(rows)
+
+
+def rcp_selftest(n: int, queue) -> int:
+    return _lib.load().magma_b200_rcp_selftest(n, _q(queue))
+
+
+def set_fused_max(n: int):
+    _lib.load().magma_b200_set_fused_max(n)
 
 
 def set_mid_max(n: int):

@@ -32,6 +32,8 @@ constexpr long MAX_CHUNK = 1L << 24;
 // Largest dimension routed to the register-file tier (lu_mid.cu); above it the blocked tier runs.
 // Measured crossover on B200 (tools/gpu_probe.py, PROBE_MID): see DESIGN.md "tiers and crossovers".
 int g_mid_max = 128;
+int g_fused_max = 0;  // largest dimension routed to the single-launch shared-memory tier (lu_fused.cu); 0 = off (default:
+                      // measured slower than the slab drivers)
 int g_host_chunk_mb = 64;  // host front ends: payload per staging buffer (MB200_HOST_CHUNK_MB overrides, for sweeps)
 
 }  // namespace
@@ -101,6 +103,8 @@ magma_int_t magma_dgetrf_batched(magma_int_t m, magma_int_t n, double **dA_array
         if (m <= 32 && n <= 32 && g_tier != 2)
             rc = lu_small_launch(d, m, n, dA_array + off, ipiv_array + off, info_array + off, 0, nullptr, 0, cnt,
                                  nullptr, s);
+        else if (m <= g_fused_max && n <= g_fused_max && g_tier != 2)
+            rc = lu_fused_launch(d, m, n, dA_array + off, ipiv_array + off, info_array + off, cnt, nullptr, s);
         else if (m <= g_mid_max && n <= g_mid_max && g_tier != 2)
             rc = lu_mid_launch(d, m, n, dA_array + off, ipiv_array + off, info_array + off, cnt, nullptr, s);
         if (rc == -100) {
@@ -565,6 +569,8 @@ void magma_idisplace_pointers(magma_int_t **output_array, magma_int_t **input_ar
 // ---------------------------------------------------------------------------------------------
 // Additions
 // ---------------------------------------------------------------------------------------------
+int64_t magma_b200_rcp_selftest(int64_t n, magma_queue_t queue) { return rcp_selftest_run((long)n, queue->stream); }
+void magma_b200_set_fused_max(int n) { g_fused_max = n > 128 ? 128 : (n < 0 ? 0 : n); }
 void magma_b200_set_mid_max(int n) { g_mid_max = n >= 128 ? 128 : (n >= 96 ? 96 : (n >= 64 ? 64 : 32)); }
 
 void magma_b200_dlarnv_uniform(magma_int_t *iseed, int64_t n, double *dx, magma_queue_t queue)

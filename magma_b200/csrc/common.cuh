@@ -33,6 +33,23 @@ extern int g_small_rows;  // register tier: rows per lane, 0 = tuned default
 
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Opt-in to more than 48 KB of dynamic shared memory. The attribute is PER DEVICE: a process that drives queues on
+// several GPUs (magma_b200_d{getrf,gesv}_batched_mgpu) must set it on each of them, so the "already done" flag is
+// kept per device, not per process.
+struct DevOnce {
+    bool set[64] = {};
+};
+template <typename F>
+inline void smem_optin(DevOnce &once, F kernel, size_t bytes)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !once.set[dev]) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (dev >= 0 && dev < 64) once.set[dev] = true;
+    }
+}
+
 // Scratch accessors (grow-only, never shrink; freed with the queue).
 void *queue_dscratch(magma_queue_t q, size_t bytes, int slot = 1);
 void *queue_hscratch(magma_queue_t q, size_t bytes);
@@ -92,6 +109,12 @@ magma_int_t lu_sq_launch(int n, double **dA, int ldda, int **dipiv, int *dinfo, 
 // lu_mid.cu: whole matrix in the register file of one CTA, 32 < max(m,n) <= 128; -100 = not covered
 magma_int_t lu_mid_launch(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo,
                           long batch, const int *index_list, cudaStream_t s);
+
+// lu_fused.cu: whole LU in one launch, matrix resident in shared memory (TMA bulk in/out), m, n <= 128; -100 = not covered
+magma_int_t lu_fused_launch(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo,
+                            long batch, const int *index_list, cudaStream_t s);
+
+long rcp_selftest_run(long n, cudaStream_t s);
 
 // lu_blocked.cu: blocked right-looking LU for any m x n (two kernels per panel step).
 // `workspace` must hold lu_blocked_workspace_bytes(batch) bytes (one 512-byte pivot record per matrix).

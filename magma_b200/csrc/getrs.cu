@@ -556,11 +556,8 @@ magma_int_t getrs_launch(int trans, int n, int nrhs, double **dA, int ldda, int 
     const int rhs_tiles = (nrhs + tr - 1) / tr;
     const long grid = batch * rhs_tiles;
     if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        cudaFuncSetAttribute(getrs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_smem = 227 * 1024;
-    }
+    static DevOnce once;
+    smem_optin(once, getrs_kernel, 227 * 1024);
     getrs_kernel<<<(unsigned)grid, SOLVE_THREADS, smem, s>>>(trans, n, nrhs, tr, dA, ldda, dipiv, dB, lddb, rhs_tiles);
     count_launch();
     MB200_CHECK_LAUNCH("getrs_kernel");
@@ -588,11 +585,8 @@ void trsm_left_launch(int uplo, int trans, int diag, int m, int n, double alpha,
         return;
     }
     const int rhs_tiles = (n + tr - 1) / tr;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(trsm_left_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr = true;
-    }
+    static DevOnce once;
+    smem_optin(once, trsm_left_kernel, 227 * 1024);
     trsm_left_kernel<<<(unsigned)(batch * rhs_tiles), SOLVE_THREADS, smem, s>>>(uplo, trans, diag, m, n, tr, alpha, dA,
                                                                               ldda, dB, lddb, rhs_tiles);
     count_launch();

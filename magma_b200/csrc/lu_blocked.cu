@@ -1452,11 +1452,8 @@ magma_int_t launch_left_update(const Dims &d, double **dA, const unsigned short 
                                int J, int finish, long batch, const int *il, cudaStream_t s)
 {
     const size_t smem = sizeof(LeftSmem<NW>);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(left_update_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    static DevOnce once;
+    smem_optin(once, left_update_kernel<NW>, smem);
     static int ahead = -1;
     if (ahead < 0) {
         const char *e = getenv("MB200_LL_AHEAD");  // tuning sweeps
@@ -1534,11 +1531,8 @@ magma_int_t launch_gemm_dmma(const Dims &d, double **dA, int k0, int rs, int cs,
 {
     if (rows_max <= 0 || cols_max <= 0) return 0;
     const size_t smem = sizeof(double) * ((size_t)KW * (DM + 4) + (size_t)DN * (KW + 4));
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(gemm_dmma_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    static DevOnce once;
+    smem_optin(once, gemm_dmma_kernel<KW>, smem);
     const int tiles_m = (rows_max + DM - 1) / DM, tiles_n = (cols_max + DN - 1) / DN;
     const long grid = (long)tiles_m * tiles_n * batch;
     if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
@@ -1646,11 +1640,8 @@ magma_int_t run_step(const Dims &d, int max_m, int max_n, double **dA, int **dip
     if (nright_max <= 0 && left_tiles == 0) return 0;
     if (mp <= SROWS && nright_max > 0) {
         // short panel: the whole trailing strip fits in shared memory
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(update_strip_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StripSmem));
-            attr_set = true;
-        }
+        static DevOnce once;
+        smem_optin(once, update_strip_kernel<32>, sizeof(StripSmem));
         const int strips = (nright_max + SW - 1) / SW;
         const long grid = (long)strips * batch;
         if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;

@@ -376,11 +376,8 @@ magma_int_t launch_mid(const Dims &d, double **dA, int **dipiv, int *dinfo, long
 {
     auto k = lu_mid_kernel<R, NW, PH, MINB>;
     const size_t smem = sizeof(MidSmem<R, NW, PH>);
-    static bool once = false;
-    if (!once) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        once = true;
-    }
+    static DevOnce once;
+    smem_optin(once, k, smem);
     k<<<(unsigned)batch, NW * 32, smem, s>>>(d, dA, dipiv, dinfo, batch, il);
     count_launch();
     MB200_CHECK_LAUNCH("lu_mid_kernel");

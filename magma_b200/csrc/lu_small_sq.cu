@@ -554,12 +554,9 @@ magma_int_t launch_sqs(double **dA, int ldda, int **dipiv, int *dinfo, double **
     const long per_cta = WC * GPW;
     const long grid = (batch + per_cta - 1) / per_cta;
     const size_t smem = NRHS ? sizeof(SqsSmem<N>) * per_cta : 0;
-    static bool once = false;
-    if (!once) {
-        cudaFuncSetAttribute(lu_sqs_kernel<N, G, NRHS, true, MINB, WC, LOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(lu_sqs_kernel<N, G, NRHS, false, MINB, WC, LOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        once = true;
-    }
+    static DevOnce once_a, once_b;
+    smem_optin(once_a, lu_sqs_kernel<N, G, NRHS, true, MINB, WC, LOCK>, smem);
+    smem_optin(once_b, lu_sqs_kernel<N, G, NRHS, false, MINB, WC, LOCK>, smem);
     if (ldda == N)
         lu_sqs_kernel<N, G, NRHS, true, MINB, WC, LOCK><<<(unsigned)grid, WC * 32, smem, s>>>(dA, dipiv, dinfo, dB, ldda, batch);
     else
@@ -578,13 +575,13 @@ magma_int_t launch_sq(double **dA, int ldda, int **dipiv, int *dinfo, double **d
     const size_t smem = sizeof(SqSmem<N, NRHS>) * per_cta;
     if (ldda == N) {
         auto k = lu_sq_kernel<N, G, R, NRHS, true, MINB>;
-        static bool once = false;
-        if (!once) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once = true; }
+        static DevOnce once;
+        smem_optin(once, k, smem);
         k<<<(unsigned)grid, WPC * 32, smem, s>>>(dA, dipiv, dinfo, dB, ldda, batch);
     } else {
         auto k = lu_sq_kernel<N, G, R, NRHS, false, MINB>;
-        static bool once = false;
-        if (!once) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once = true; }
+        static DevOnce once;
+        smem_optin(once, k, smem);
         k<<<(unsigned)grid, WPC * 32, smem, s>>>(dA, dipiv, dinfo, dB, ldda, batch);
     }
     count_launch();

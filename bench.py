@@ -32,6 +32,19 @@ N_HEAD, NRHS_HEAD, BATCH_HEAD = 16, 1, 1_000_000
 KERNEL_HEAD = "lu_sqs_kernel<16,8,1>"  # the one kernel a headline step launches (magma_b200/csrc/lu_small_sq.cu)
 
 
+def advance_seed(iseed, ndraws):
+    """LAPACK dlarnv seed after ndraws draws (x <- a x mod 2^48, a = 33952834046453; base-4096 digits)."""
+    import numpy as np
+    x = (int(iseed[0]) << 36) | (int(iseed[1]) << 24) | (int(iseed[2]) << 12) | int(iseed[3])
+    x = (x * pow(33952834046453, int(ndraws), 1 << 48)) & ((1 << 48) - 1)
+    return np.array([(x >> 36) & 4095, (x >> 24) & 4095, (x >> 12) & 4095, x & 4095], dtype=np.int32)
+
+
+def workload_str(batch):
+    """config.workload: the SAME string in both arms (the driver compares them)."""
+    return f"dgesv_batched n={N_HEAD} nrhs={NRHS_HEAD} batch={batch} per GPU (BASELINE configs[1])"
+
+
 def flops_getrf(m, n):
     if m < n:
         mul = 0.5 * m * (m * (n - m / 3.0 - 1.0) + n) + 2.0 * m / 3.0
@@ -154,7 +167,7 @@ def reference_arm(args):
     vals, secs = [], []
     cores = sample = desc = None
     for i in range(args.warmup + args.steps):
-        g, cores, sample, t, desc = cpu_lapack_gesv(N_HEAD, NRHS_HEAD, BATCH_HEAD, budget_s=4.0)
+        g, cores, sample, t, desc = cpu_lapack_gesv(N_HEAD, NRHS_HEAD, args.batch, budget_s=4.0)
         if i >= args.warmup:
             vals.append(g)
             secs.append(t)
@@ -164,10 +177,10 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"dgesv_batched n={N_HEAD} nrhs={NRHS_HEAD} batch={BATCH_HEAD} per GPU",
+        "config": {"workload": workload_str(args.batch),
                    "inputs": "dlarnv(1,{0,0,0,1})", "step": f"LAPACK dgesv loop over a {sample}-matrix sample"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": f"{sample} of {BATCH_HEAD} matrices per step; omp parallel for schedule(dynamic) "
+                         "sample": f"{sample} of {args.batch} matrices per step; omp parallel for schedule(dynamic) "
                                    f"over dgesv_, BLAS threads = 1 ({desc})"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -185,6 +198,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ref", action="store_true", help="skip the same-box reference-GPU / cuBLAS rows")
     ap.add_argument("--batch", type=int, default=BATCH_HEAD)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -318,10 +332,30 @@ def main():
             e2e_t.append(max_over_ranks(dt))
     clocks.stop()
     assert int(hinfo.abs().max()) == 0
+    # the box's host<->device ceiling for the same bytes: H2D and D2H of one step's payload on two streams, no compute
+    # (what the host side -- pinned memory bandwidth and the PCIe root complexes the ranks share -- allows at this N)
+    dscr = torch.empty((batch, n + nrhs, n), dtype=torch.float64, device=dev)
+    s_in, s_out = torch.cuda.Stream(local), torch.cuda.Stream(local)
+    copy_t = []
+    for i in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_in):
+            dscr[:, :n].copy_(hA, non_blocking=True)
+            dscr[:, n:].copy_(hB, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hA.copy_(dscr[:, :n], non_blocking=True)
+            hB.copy_(dscr[:, n:], non_blocking=True)
+        torch.cuda.synchronize()
+        copy_t.append(max_over_ranks(time.perf_counter() - t0))
+    del dscr
     e2e_val = fl_mat * batch * world / (sum(e2e_t) / len(e2e_t)) / 1e9
     e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": (n * n + n * nrhs) * 8 * batch,
            "d2h_bytes_per_step": ((n * n + n * nrhs) * 8 + n * 4 + 4) * batch,
            "ms_per_step": 1e3 * sum(e2e_t) / len(e2e_t),
+           "pcie_GBs_per_rank": ((n * n + n * nrhs) * 16 + n * 4 + 4) * batch / (sum(e2e_t) / len(e2e_t)) / 1e9,
+           "copy_only_ms": 1e3 * min(copy_t),
+           "copy_only_note": "same bytes both ways on two streams with no kernel: the host-side ceiling at this rank count",
            "call": "magma_b200_dgesv_batched_host (pinned host A,B in; LU,X,ipiv,info out)"}
     del hA, hB, hA0, hB0, hip, hinfo
 
@@ -337,6 +371,13 @@ def main():
         sweep = run_sweep(mb, torch, np, q, local, rank, world, barrier, max_over_ranks, sum_over_ranks, hbm_peak,
                           fp64_peak)
 
+    strong = None
+    if world > 1 and not args.no_sweep:
+        strong = run_strong(mb, torch, np, q, local, rank, world, barrier, max_over_ranks, dist, dev)
+    ref_gpu = None
+    if rank == 0 and world == 1 and not args.no_sweep and not args.no_ref:
+        ref_gpu = run_ref_gpu(sweep, e2e=None, head_ms=total_ms / K)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         g, cores, cnt, t, desc = cpu_lapack_gesv(n, nrhs, batch)
@@ -349,13 +390,13 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"dgesv_batched n={n} nrhs={nrhs} batch={batch} per GPU (BASELINE configs[1])",
+            "config": {"workload": workload_str(batch),
                        "inputs": f"dlarnv U(0,1) generated in HBM; {nbuf} distinct batches of "
                                  f"{(by_mat // 2) * batch / 1e9:.2f} GB (> L2) rotated, ldda=lddb=n",
                        "parallelism": f"batch sharded by matrix index over {world} GPU(s), no collective",
                        "l2": "inputs larger than L2"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(gpu_launches),
-            "clocks": clocks.summary(), "peaks": peaks, "sweep": sweep,
+            "clocks": clocks.summary(), "peaks": peaks, "sweep": sweep, "strong": strong, "ref_gpu": ref_gpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -423,7 +464,41 @@ def run_sweep(mb, torch, np, q, local, rank, world, barrier, max_over_ranks, sum
         del db, A0, B0
         torch.cuda.empty_cache()
 
-    fixed("C1 dgetrf_batched n=32 batch=10000", 32, 10_000, reps=9)
+    # C1 is an 80 us call: 25 timed calls over four rotated 164 MB batches (each restored outside the timed region;
+    # together 650 MB > L2), median -- one launch per call, so launch latency is part of the number, as for a user
+    def c1(name, n, batch, nbuf=4, reps=25):
+        dbs = [mb.DeviceBatch(batch, n, n, device=local, queue=q) for _ in range(nbuf)]
+        A0s = []
+        for i, db in enumerate(dbs):
+            seed = np.array([11 + i, rank, 0, 1], dtype=np.int32)
+            mb.dlarnv_uniform(seed, batch * n * n, db.A, q)
+        q.sync()
+        A0s = [db.A.clone() for db in dbs]
+        ts = []
+        for r in range(reps + 3):
+            i = r % nbuf
+            dbs[i].A.copy_(A0s[i])
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rc = dbs[i].getrf()
+            e1.record(stream)
+            barrier()
+            assert rc == 0
+            if r >= 3:
+                ts.append(max_over_ranks(e0.elapsed_time(e1)))
+        ts.sort()
+        med, best = ts[len(ts) // 2], ts[0]
+        gf = flops_getrf(n, n) * batch * world / (med * 1e-3) / 1e9
+        roof = min(flops_getrf(n, n) / (16.0 * n * n) * hbm_peak, fp64_peak)
+        out.append({"config": name, "n": n, "batch_per_gpu": batch, "ms": med, "ms_best": best, "gflops": gf,
+                    "gflops_per_gpu": gf / world, "roofline_gflops": roof, "bound": "hbm", "frac_of_roofline": gf / world / roof,
+                    "alg_GBs_per_gpu": 16.0 * n * n * batch / (med * 1e-3) / 1e9, "launches_per_call": 1,
+                    "timing": f"median of {reps} calls over {nbuf} rotated batches", "info_max": int(dbs[0].info.abs().max().item())})
+        del dbs, A0s
+        torch.cuda.empty_cache()
+
+    c1("C1 dgetrf_batched n=32 batch=10000", 32, 10_000)
     fixed("C1b dgetrf_batched n=32 batch=1000000", 32, 1_000_000)
     fixed("C3 dgetrf_batched n=128 batch=50000", 128, 50_000)
     fixed("C5 dgetrf_batched n=512 batch=4000 (+dgetrs nrhs=16)", 512, 4_000, nrhs=16, solve_after=True, reps=3)
@@ -502,6 +577,133 @@ def run_sweep(mb, torch, np, q, local, rank, world, barrier, max_over_ranks, sum
                 "alg_GBs_per_gpu": 16.0 * float((ns * ns).sum()) / (med * 1e-3) / 1e9,
                 "info_max": int(dinfo.abs().max().item())})
     return out
+
+
+def run_strong(mb, torch, np, q, local, rank, world, barrier, max_over_ranks, dist, dev):
+    """STRONG scaling (north_star: "the batch is sharded across the GPUs of one box by matrix index, with per-GPU
+    queues and no NCCL collective"): ONE batch of the BASELINE size, rank r owns mgpu.shard_range(batch, world, r).
+    t_full = the same call over the whole batch on one GPU (every rank runs it at once on its own GPU; max taken),
+    efficiency = t_full / (world * t_shard). C4: ONE 20,000-matrix vbatched batch, LPT partition by LU cost."""
+    from magma_b200 import mgpu
+    stream = torch.cuda.current_stream(local)
+    rows = []
+
+    def timed(fn, restore, reps=3):
+        ts = []
+        for _ in range(reps):
+            restore()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rc = fn()
+            e1.record(stream)
+            barrier()
+            assert rc == 0
+            ts.append(e0.elapsed_time(e1))
+        return min(ts)
+
+    def fixed(name, n, batch, nrhs=0):
+        lo, hi = mgpu.shard_range(batch, world, rank)
+        res = {}
+        for tag, cnt in (("full", batch), ("shard", hi - lo)):
+            db = mb.DeviceBatch(cnt, n, n, nrhs=nrhs, device=local, queue=q)
+            seed = np.array([17, 0, 0, 1], dtype=np.int32)  # the SAME global batch on every rank ...
+            if tag == "shard" and lo > 0:                   # ... of which this rank takes [lo, hi): skip lo matrices
+                seed = advance_seed(seed, lo * n * n)
+            mb.dlarnv_uniform(seed, cnt * n * n, db.A, q)
+            if nrhs:
+                mb.dlarnv_uniform(np.array([19, rank, 0, 1], dtype=np.int32), cnt * n * nrhs, db.B, q)
+            q.sync()
+            A0 = db.A.clone()
+            B0 = db.B.clone() if nrhs else None
+
+            def restore():
+                db.A.copy_(A0)
+                if nrhs:
+                    db.B.copy_(B0)
+            t = timed(db.gesv if nrhs else db.getrf, restore)
+            res[tag] = max_over_ranks(t)
+            del db, A0, B0
+            torch.cuda.empty_cache()
+        fl = (flops_getrf(n, n) + (flops_getrs(n, nrhs) if nrhs else 0)) * batch
+        rows.append({"config": name, "total_batch": batch, "ms_one_gpu": res["full"], "ms_sharded": res["shard"],
+                     "gflops_sharded": fl / (res["shard"] * 1e-3) / 1e9, "speedup": res["full"] / res["shard"],
+                     "strong_efficiency": res["full"] / (world * res["shard"])})
+
+    fixed("C2 dgesv_batched n=16 nrhs=1, ONE batch of 1000000", N_HEAD, BATCH_HEAD, nrhs=NRHS_HEAD)
+    fixed("C3 dgetrf_batched n=128, ONE batch of 50000", 128, 50_000)
+    fixed("C5 dgetrf_batched n=512, ONE batch of 4000", 512, 4_000)
+
+    # C4: one batch for the whole box, partitioned by LU cost (mgpu.lpt_partition)
+    batch = 20_000
+    x, ns = 1234, []
+    for _ in range(batch):
+        x = (x * 1103515245 + 12345) & 0x7FFFFFFF
+        ns.append(16 + (x >> 8) % 497)
+    ns = np.array(ns, dtype=np.int64)
+    for scheme in ("lpt", "contiguous"):
+        parts = mgpu.lpt_partition(ns, ns, world) if scheme == "lpt" else \
+            [np.arange(*mgpu.shard_range(batch, world, r)) for r in range(world)]
+        mine = ns[parts[rank]]
+        offs = np.concatenate([[0], np.cumsum(mine * mine)])
+        poffs = np.concatenate([[0], np.cumsum(mine)])
+        dA = torch.empty(int(offs[-1]), dtype=torch.float64, device=dev)
+        mb.dlarnv_uniform(np.array([21, rank, 0, 1], dtype=np.int32), int(offs[-1]), dA, q)
+        q.sync()
+        A0 = dA.clone()
+        dip = torch.zeros(int(poffs[-1]), dtype=torch.int32, device=dev)
+        dinfo = torch.zeros(len(mine), dtype=torch.int32, device=dev)
+        pA = torch.from_numpy(offs[:-1] * 8).to(dev) + dA.data_ptr()
+        pP = torch.from_numpy(poffs[:-1] * 4).to(dev) + dip.data_ptr()
+        dn = torch.from_numpy(mine.astype(np.int32)).to(dev)
+        t = timed(lambda: mb.magma_dgetrf_vbatched(dn, dn, pA, dn, pP, dinfo, len(mine), q), lambda: dA.copy_(A0))
+        tt = torch.tensor([t], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allt, tt)
+        allt = [float(v.item()) for v in allt]
+        fl = float(sum(flops_getrf(int(k), int(k)) for k in ns))
+        rows.append({"config": f"C4 dgetrf_vbatched n~U[16,512], ONE batch of 20000, {scheme} partition",
+                     "ms_per_rank": allt, "ms": max(allt), "gflops": fl / (max(allt) * 1e-3) / 1e9,
+                     "time_imbalance_max_over_mean": max(allt) / (sum(allt) / world),
+                     "cost_model_imbalance": mgpu.imbalance(ns, ns, parts)})
+        del dA, A0, dip, dinfo
+        torch.cuda.empty_cache()
+    return rows
+
+
+def run_ref_gpu(sweep, e2e, head_ms):
+    """Same-box rows for the reference's own GPU path (oracle/_ref/libmagma_ref.so: MAGMA 2.10.0 kernels + cuBLAS,
+    compiled by oracle/build_ref.py) and cublasDgetrfBatched, each in a child process (the
+    reference exports the same symbol names as this library). Timed the way the reference testers time: wall clock
+    around a queue sync, best of 3 (testing/testing_zgetrf_batched.cpp:203-206,233-249); ours: CUDA events."""
+    import subprocess
+    so = os.path.join(ROOT, "oracle", "_ref", "libmagma_ref.so")
+    tool = os.path.join(ROOT, "tools", "ref_run.py")
+    if not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/libmagma_ref.so not built (python oracle/build_ref.py needs /root/reference)"}
+    ours = {r["config"].split()[0]: r for r in sweep}
+    rows = []
+    for tag, n, batch, nrhs, our_ms in (("C1", 32, 10_000, 0, ours.get("C1", {}).get("ms")),
+                                        ("C2", 16, 1_000_000, 1, head_ms),
+                                        ("C3", 128, 50_000, 0, ours.get("C3", {}).get("ms")),
+                                        ("C5", 512, 4_000, 0, ours.get("C5", {}).get("ms"))):
+        row = {"config": tag, "n": n, "batch": batch, "nrhs": nrhs, "ours_ms": our_ms}
+        for impl in ("magma", "cublas"):
+            if impl == "cublas" and nrhs:
+                continue
+            try:
+                r = subprocess.run([sys.executable, tool, str(n), str(batch), str(nrhs), "-", "3", "tile", impl],
+                                   capture_output=True, text=True, timeout=600)
+                js = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                ms = json.loads(js[-1])["ms_best"] if js else None
+            except Exception as ex:  # noqa: BLE001
+                ms = None
+                row[impl + "_error"] = str(ex)[:200]
+            row[impl + "_ms"] = ms
+            if ms and our_ms:
+                row["ours_over_" + impl] = ms / our_ms
+        rows.append(row)
+    return rows
 
 
 if __name__ == "__main__":

@@ -1,0 +1,463 @@
+"""GPU tests added in round 2 (run with -m gpu on the B200 box), all through the C ABI:
+  * the single-launch shared-memory tier (lu_fused.cu), forced on over its whole range,
+  * the panel-level / BLAS-level source-compatibility entry points (compat.cu),
+  * the single-process multi-GPU entry points on two devices,
+  * shapes the round-1 suite never reached (tall panels up to 9000 rows, n = 1024, batchCount > 2^24),
+  * the compiled reference GPU path (oracle/_ref, run in a child process) as a second witness,
+  * a C program compiled and LINKED against libmagma_b200.so that walks the tester sequence.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from magma_b200 import _lib
+from magma_b200 import batched as mb
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from test_gpu_parity import check_against_oracle, run_getrf  # noqa: E402
+
+
+# ---- single-launch tier --------------------------------------------------------------------------------------
+
+@pytest.fixture
+def fused_tier():
+    mb.set_fused_max(128)
+    yield
+    mb.set_fused_max(0)
+
+
+def test_rcp_selftest(gpu_queue):
+    """The chain's inline reciprocal equals IEEE 1.0/x bit for bit on 50M pseudo-random inputs."""
+    assert mb.rcp_selftest(50_000_000, gpu_queue) == 0
+
+
+@pytest.mark.parametrize("m,n,batch", [(128, 128, 9), (64, 64, 9), (40, 40, 11), (33, 33, 7), (65, 65, 7), (96, 96, 5),
+                                       (100, 100, 5), (127, 127, 4), (128, 64, 5), (64, 128, 5), (128, 72, 4), (72, 128, 4),
+                                       (97, 113, 4), (113, 97, 4), (48, 120, 4), (120, 48, 4), (128, 8, 4), (8, 128, 4),
+                                       (128, 1, 3), (1, 128, 3), (70, 66, 4), (66, 70, 4), (128, 104, 3), (35, 90, 3)])
+def test_fused_tier(gpu_queue, fused_tier, m, n, batch):
+    A0, _ = oracle.random_batch(batch, m, n)
+    check_against_oracle(gpu_queue, A0, m)
+
+
+@pytest.mark.parametrize("m,n,ldda", [(128, 128, 130), (128, 128, 129), (100, 100, 101), (64, 64, 72), (127, 127, 128),
+                                      (90, 90, 90)])
+def test_fused_tier_ldda(gpu_queue, fused_tier, m, n, ldda):
+    """Even/aligned shapes take the TMA bulk path, odd leading dimensions and odd row counts the plain-load path."""
+    A0, _ = oracle.random_batch(4, m, n)
+    check_against_oracle(gpu_queue, A0, m, ldda=ldda)
+
+
+def test_fused_tier_singular_and_ties(gpu_queue, fused_tier):
+    rng = np.random.default_rng(5)
+    for n in (40, 72, 128):
+        mats = [np.zeros((n, n)), np.ones((n, n)), np.eye(n), np.fliplr(np.eye(n)),
+                rng.integers(-3, 4, size=(n, n)).astype(float)]
+        Z = rng.random((n, n))
+        Z[:, n // 3] = 0.0
+        mats.append(Z)
+        Z2 = rng.random((n, n))
+        Z2[n // 2:, :] = Z2[:n - n // 2, :]
+        mats.append(Z2)
+        Z3 = rng.random((n, n)) * 1e-305  # pivots below 2^-999: the reciprocal's out-of-range branch (1/x still finite)
+        mats.append(Z3)
+        Z4 = rng.random((n, n)) * 1e300
+        mats.append(Z4)
+        check_against_oracle(gpu_queue, np.stack(mats), n)
+
+
+def test_fused_tier_full_size_sample(gpu_queue, fused_tier):
+    """C3 shape at a batch that fills the GPU several times over: bit-exact sample + residual on all."""
+    n, batch = 128, 3000
+    A0, _ = oracle.random_batch(batch, n, n)
+    check_against_oracle(gpu_queue, A0, n)
+
+
+# ---- source-compatibility entry points ---------------------------------------------------------------------------
+
+def _panel_case(q, fn_name, m, n, ai, batch=5, M=150, N=70):
+    """Factor the m x n block at (ai, ai) of M x N matrices through one of the panel entry points."""
+    import torch
+    L = _lib.load()
+    A0, _ = oracle.random_batch(batch, M, N)
+    db = mb.DeviceBatch(batch, M, N, queue=q)
+    db.upload(A0)
+    db.info.fill_(0)
+    dummy = torch.zeros(batch, dtype=torch.int64, device="cuda")
+    if fn_name == "magma_dgetf2_fused_batched":
+        rc = L.magma_dgetf2_fused_batched(m, n, mb.ptr(db.dA_array), ai, ai, M, mb.ptr(db.dipiv_array), mb.ptr(db.info), batch,
+                                          q.handle)
+    elif fn_name == "magma_dgetf2_batched":
+        rc = L.magma_dgetf2_batched(m, n, mb.ptr(db.dA_array), ai, ai, M, mb.ptr(db.dipiv_array), mb.ptr(dummy),
+                                    mb.ptr(db.info), ai, batch, q.handle)
+    else:
+        rc = L.magma_dgetrf_recpanel_batched(m, n, 32, mb.ptr(db.dA_array), ai, ai, M, mb.ptr(db.dipiv_array),
+                                             mb.ptr(dummy), mb.ptr(db.info), ai, batch, q.handle)
+    assert rc == 0
+    q.sync()
+    LU = db.A.cpu().numpy()
+    ipiv = db.ipiv.cpu().numpy()
+    # oracle on the block alone
+    blk = np.ascontiguousarray(A0[:, ai:ai + n, ai:ai + m]).copy()
+    ipr, infr = oracle.getrf_batched(blk, m)
+    assert np.array_equal(LU[:, ai:ai + n, ai:ai + m], blk), "panel factors differ"
+    assert np.array_equal(ipiv[:, ai:ai + min(m, n)], ipr), "panel pivots must be relative to row ai"
+    # nothing outside the block is touched
+    mask = np.ones_like(A0, dtype=bool)
+    mask[:, ai:ai + n, ai:ai + m] = False
+    assert np.array_equal(LU[mask], A0[mask])
+    assert np.array_equal(db.info.cpu().numpy(), np.where(infr != 0, infr + ai, 0))
+
+
+@pytest.mark.parametrize("fn", ["magma_dgetf2_fused_batched", "magma_dgetf2_batched", "magma_dgetrf_recpanel_batched"])
+@pytest.mark.parametrize("m,n,ai", [(150, 32, 0), (118, 32, 32), (86, 6, 64), (40, 8, 20)])
+def test_panel_entry_points(gpu_queue, fn, m, n, ai):
+    _panel_case(gpu_queue, fn, m, n, ai)
+
+
+def test_recpanel_wide_panel(gpu_queue):
+    _panel_case(gpu_queue, "magma_dgetrf_recpanel_batched", 120, 64, 6)
+
+
+def test_getf2_fused_rejects_wide(gpu_queue):
+    L = _lib.load()
+    assert L.magma_dgetf2_fused_batched(64, 33, 0, 0, 0, 64, 0, 0, 1, gpu_queue.handle) == -2
+
+
+def test_panel_info_merge(gpu_queue):
+    """A zero column inside the block records gbstep + step + 1 unless an earlier panel already recorded one."""
+    import torch
+    L = _lib.load()
+    M = 64
+    A0, _ = oracle.random_batch(3, M, M)
+    A0[:, 20, :] = 0.0  # column 20 is exactly zero
+    db = mb.DeviceBatch(3, M, M, queue=gpu_queue)
+    db.upload(A0)
+    db.info.copy_(torch.tensor([0, 7, 0], dtype=torch.int32))
+    assert L.magma_dgetf2_fused_batched(M - 16, 16, mb.ptr(db.dA_array), 16, 16, M, mb.ptr(db.dipiv_array), mb.ptr(db.info), 3,
+                                        gpu_queue.handle) == 0
+    gpu_queue.sync()
+    assert db.info.cpu().tolist() == [21, 7, 21]
+
+
+def test_laswp_rowparallel(gpu_queue):
+    """new[r] = old[pivinfo[r]-1] for the top rows (to the output) and for the rows they came from (in place)."""
+    import torch
+    L = _lib.load()
+    batch, m, n, h = 4, 50, 19, 8
+    rng = np.random.default_rng(3)
+    A0 = rng.random((batch, n, m))
+    piv = np.zeros((batch, m), dtype=np.int32)
+    for b in range(batch):
+        # permutation as setup_pivinfo builds it from h sequential interchanges
+        p = np.arange(m)
+        for i in range(h):
+            j = rng.integers(i, m)
+            p[[i, j]] = p[[j, i]]
+        piv[b] = p + 1
+    dA = torch.from_numpy(A0).cuda()
+    dP = torch.from_numpy(piv).cuda()
+    pA = torch.tensor([dA.data_ptr() + b * n * m * 8 for b in range(batch)], dtype=torch.int64, device="cuda")
+    pP = torch.tensor([dP.data_ptr() + b * m * 4 for b in range(batch)], dtype=torch.int64, device="cuda")
+    L.magma_dlaswp_rowparallel_batched(n, mb.ptr(pA), 0, 0, m, mb.ptr(pA), 0, 0, m, 0, h, mb.ptr(pP), batch, gpu_queue.handle)
+    gpu_queue.sync()
+    out = dA.cpu().numpy()
+    for b in range(batch):
+        p = piv[b] - 1
+        exp = A0[b].copy()
+        touched = set(range(h)) | set(p[:h].tolist())
+        for r in touched:
+            exp[:, r] = A0[b][:, p[r]]
+        assert np.array_equal(out[b], exp)
+
+
+@pytest.mark.parametrize("uplo", [mb.MagmaLower, mb.MagmaUpper])
+@pytest.mark.parametrize("trans", [mb.MagmaNoTrans, mb.MagmaTrans])
+@pytest.mark.parametrize("diag", [mb.MagmaUnit, mb.MagmaNonUnit])
+@pytest.mark.parametrize("n,incb", [(1, 1), (31, 1), (32, 2), (100, 1), (257, 3)])
+def test_trsv_batched(gpu_queue, uplo, trans, diag, n, incb):
+    import torch
+    L = _lib.load()
+    batch = 3
+    rng = np.random.default_rng(n)
+    A = rng.random((batch, n, n)) + n * np.eye(n)  # [b, col, row], well conditioned
+    x0 = rng.random((batch, n * incb))
+    dA = torch.from_numpy(A).cuda()
+    dx = torch.from_numpy(x0).cuda()
+    pA = torch.tensor([dA.data_ptr() + b * n * n * 8 for b in range(batch)], dtype=torch.int64, device="cuda")
+    px = torch.tensor([dx.data_ptr() + b * n * incb * 8 for b in range(batch)], dtype=torch.int64, device="cuda")
+    L.magmablas_dtrsv_batched(uplo, trans, diag, n, mb.ptr(pA), n, mb.ptr(px), incb, batch, gpu_queue.handle)
+    gpu_queue.sync()
+    x = dx.cpu().numpy()
+    for b in range(batch):
+        M = A[b].T  # M[row, col]
+        T = np.tril(M) if uplo == mb.MagmaLower else np.triu(M)
+        if diag == mb.MagmaUnit:
+            np.fill_diagonal(T, 1.0)
+        if trans != mb.MagmaNoTrans:
+            T = T.T
+        ref = np.linalg.solve(T, x0[b, ::incb])
+        assert np.allclose(x[b, ::incb], ref, rtol=1e-11, atol=1e-13)
+        if incb > 1:  # the gaps are untouched
+            keep = np.ones(n * incb, dtype=bool)
+            keep[::incb] = False
+            assert np.array_equal(x[b][keep], x0[b][keep])
+
+
+# ---- single-process multi-GPU -------------------------------------------------------------------------------------
+
+def _two_gpus():
+    import torch
+    return torch.cuda.device_count() >= 2
+
+
+@pytest.mark.parametrize("n", [16, 128, 200])
+def test_mgpu_getrf_two_devices(n):
+    """magma_b200_dgetrf_batched_mgpu over per-device queues: kernels that opt in to > 48 KB of shared memory must
+    do so on EVERY device (the attribute is per device), and each shard must equal the oracle bit for bit."""
+    if not _two_gpus():
+        pytest.skip("needs 2 GPUs")
+    import torch
+    from magma_b200 import mgpu
+    L = _lib.load()
+    assert mb.magma_init() == 0
+    batch = 37
+    A0, _ = oracle.random_batch(batch, n, n)
+    ref = A0.copy()
+    ipr, infr = oracle.getrf_batched(ref, n)
+    ngpu = 2
+    queues, dbs, cnts = [], [], []
+    for g in range(ngpu):
+        torch.cuda.set_device(g)
+        q = mb.Queue(g)
+        lo, hi = mgpu.shard_range(batch, ngpu, g)
+        db = mb.DeviceBatch(hi - lo, n, n, device=g, queue=q)
+        db.upload(A0[lo:hi])
+        queues.append(q); dbs.append(db); cnts.append(hi - lo)
+    torch.cuda.set_device(0)
+    PP = C.c_void_p * ngpu
+    dA = PP(*[db.dA_array.data_ptr() for db in dbs])
+    dP = PP(*[db.dipiv_array.data_ptr() for db in dbs])
+    dI = PP(*[db.info.data_ptr() for db in dbs])
+    cn = (C.c_int * ngpu)(*cnts)
+    qs = PP(*[q.handle for q in queues])
+    rc = L.magma_b200_dgetrf_batched_mgpu(ngpu, n, n, C.addressof(dA), n, C.addressof(dP), C.addressof(dI), C.addressof(cn),
+                                          C.addressof(qs))
+    assert rc == 0
+    for g in range(ngpu):
+        torch.cuda.set_device(g)
+        queues[g].sync()
+        torch.cuda.synchronize(g)
+        lo, hi = mgpu.shard_range(batch, ngpu, g)
+        assert np.array_equal(dbs[g].ipiv.cpu().numpy()[:, :n], ipr[lo:hi]), f"device {g}"
+        assert np.array_equal(dbs[g].A.cpu().numpy(), ref[lo:hi]), f"device {g}"
+        assert np.array_equal(dbs[g].info.cpu().numpy(), infr[lo:hi])
+    torch.cuda.set_device(0)
+
+
+def test_mgpu_gesv_two_devices():
+    if not _two_gpus():
+        pytest.skip("needs 2 GPUs")
+    import torch
+    from magma_b200 import mgpu
+    L = _lib.load()
+    n, nrhs, batch = 96, 3, 21
+    A0, seed = oracle.random_batch(batch, n, n)
+    B0, _ = oracle.random_batch(batch, n, nrhs, iseed=seed)
+    Ar, Br = A0.copy(), B0.copy()
+    ipr, infr = oracle.gesv_batched(Ar, Br, n)
+    ngpu = 2
+    queues, dbs, cnts = [], [], []
+    for g in range(ngpu):
+        torch.cuda.set_device(g)
+        q = mb.Queue(g)
+        lo, hi = mgpu.shard_range(batch, ngpu, g)
+        db = mb.DeviceBatch(hi - lo, n, n, nrhs=nrhs, device=g, queue=q)
+        db.upload(A0[lo:hi], B0[lo:hi])
+        queues.append(q); dbs.append(db); cnts.append(hi - lo)
+    torch.cuda.set_device(0)
+    PP = C.c_void_p * ngpu
+    arr = lambda f: PP(*[f(db) for db in dbs])  # noqa: E731
+    dA, dP, dB, dI = arr(lambda d: d.dA_array.data_ptr()), arr(lambda d: d.dipiv_array.data_ptr()), \
+        arr(lambda d: d.dB_array.data_ptr()), arr(lambda d: d.info.data_ptr())
+    cn = (C.c_int * ngpu)(*cnts)
+    qs = PP(*[q.handle for q in queues])
+    rc = L.magma_b200_dgesv_batched_mgpu(ngpu, n, nrhs, C.addressof(dA), n, C.addressof(dP), C.addressof(dB), n,
+                                         C.addressof(dI), C.addressof(cn), C.addressof(qs))
+    assert rc == 0
+    for g in range(ngpu):
+        torch.cuda.set_device(g)
+        queues[g].sync()
+        torch.cuda.synchronize(g)
+        lo, hi = mgpu.shard_range(batch, ngpu, g)
+        assert np.array_equal(dbs[g].B.cpu().numpy(), Br[lo:hi]), f"device {g}"
+    torch.cuda.set_device(0)
+
+
+# ---- ranges round 1 never reached ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("m,n,batch", [(1536, 16, 2), (1536, 40, 2), (3000, 24, 2), (5000, 16, 1), (5000, 40, 1), (9000, 16, 1),
+                                       (9000, 33, 1), (2049, 8, 2)])
+def test_tall_panels(gpu_queue, m, n, batch):
+    """R = 4 / 8 / 16 register panels (1025..8192 rows) and the global-memory panel above 8192 rows."""
+    A0, _ = oracle.random_batch(batch, m, n)
+    check_against_oracle(gpu_queue, A0, m)
+
+
+def test_square_1024(gpu_queue):
+    """Right-looking driver over many steps (more than 512 rows)."""
+    A0, _ = oracle.random_batch(2, 1024, 1024)
+    check_against_oracle(gpu_queue, A0, 1024)
+
+
+def test_wide_600x1500(gpu_queue):
+    A0, _ = oracle.random_batch(2, 600, 1500)
+    check_against_oracle(gpu_queue, A0, 600)
+
+
+def test_batchcount_above_2_24(gpu_queue):
+    """One call with more matrices than a launch chunk (2^24): the chunk loop. n = 2: 16.8M x 32 bytes."""
+    import torch
+    n = 2
+    batch = (1 << 24) + 1000
+    db = mb.DeviceBatch(batch, n, n, queue=gpu_queue)
+    seed = np.array([0, 0, 0, 1], dtype=np.int32)
+    mb.dlarnv_uniform(seed, batch * n * n, db.A, gpu_queue)
+    gpu_queue.sync()
+    A0 = db.A.clone()
+    assert db.getrf() == 0
+    gpu_queue.sync()
+    # 2 x 2 LU in closed form on the device, every matrix: pivot = larger first-column entry
+    a, c, b, d = A0[:, 0, 0], A0[:, 0, 1], A0[:, 1, 0], A0[:, 1, 1]   # A[b, col, row]
+    swap = c.abs() > a.abs()
+    p = torch.where(swap, c, a)
+    lo = torch.where(swap, a, c)
+    u01 = torch.where(swap, d, b)
+    r1 = torch.where(swap, b, d)
+    l = lo * (1.0 / p)
+    u11 = torch.addcmul(r1, -l, u01)  # not fused on every backend: compare with a tolerance of 1 ulp
+    assert torch.equal(db.A[:, 0, 0], p) and torch.equal(db.A[:, 0, 1], l) and torch.equal(db.A[:, 1, 0], u01)
+    assert torch.allclose(db.A[:, 1, 1], u11, rtol=4e-16, atol=0)
+    assert torch.equal(db.ipiv[:, 0], torch.where(swap, 2, 1).to(torch.int32))
+    assert torch.equal(db.ipiv[:, 1], torch.full_like(db.ipiv[:, 1], 2))
+    assert int(db.info.abs().max()) == 0
+    # the tail beyond the first chunk against the oracle, bit for bit
+    tail = A0[(1 << 24) - 8:].cpu().numpy()
+    ref = tail.copy()
+    ipr, _ = oracle.getrf_batched(ref, n)
+    assert np.array_equal(db.A[(1 << 24) - 8:].cpu().numpy(), ref)
+    assert np.array_equal(db.ipiv[(1 << 24) - 8:].cpu().numpy(), ipr)
+
+
+# ---- the compiled reference GPU path as a second witness ------------------------------------------------------------------
+
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libmagma_ref.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libmagma_ref.so not built (oracle/build_ref.py)")
+@pytest.mark.parametrize("n,batch,nrhs", [(32, 1000, 0), (16, 4000, 1), (128, 100, 0), (512, 6, 0), (512, 4, 16)])
+def test_against_reference_gpu(gpu_queue, tmp_path, n, batch, nrhs):
+    """Same dlarnv inputs through MAGMA 2.10.0's own kernels (+cuBLAS), run in a child process because both
+    libraries export the same names: pivots identical, both inside the testers' 30 eps backward-error bar."""
+    out = tmp_path / "ref.npz"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_run.py"), str(n), str(batch), str(nrhs), str(out)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = np.load(out)
+    A0, seed = oracle.random_batch(batch, n, n)
+    if nrhs:
+        B0, _ = oracle.random_batch(batch, n, nrhs, iseed=seed)
+        db = mb.DeviceBatch(batch, n, n, nrhs=nrhs, queue=gpu_queue)
+        db.upload(A0, B0)
+        assert db.gesv() == 0
+        LU, ipiv, info, X = db.download()
+        assert oracle.solve_residual(oracle.MagmaNoTrans, A0, X, B0, n) < oracle.TOL
+        assert oracle.solve_residual(oracle.MagmaNoTrans, A0, ref["X"], B0, n) < oracle.TOL
+    else:
+        LU, ipiv, info = run_getrf(gpu_queue, A0, n)
+    assert np.array_equal(ipiv, ref["ipiv"]), "pivots differ from the reference's GPU path"
+    assert np.array_equal(info, ref["info"])
+    assert oracle.lu_backward_error(A0, LU, ipiv, n) < oracle.TOL
+    assert oracle.lu_backward_error(A0, ref["LU"], ref["ipiv"], n) < oracle.TOL
+    # same algorithm, different summation order in the trailing update: factors agree to rounding
+    scale = np.max(np.abs(ref["LU"]))
+    assert np.max(np.abs(LU - ref["LU"])) <= 1e-9 * scale
+
+
+# ---- a C program linked against the library -----------------------------------------------------------------------------------
+
+C_PROG = r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include "magma_v2.h"
+/* testing/testing_zgetrf_batched.cpp:161-206 (z -> d): allocate, set pointers, factor, copy back */
+int main(void)
+{
+    magma_int_t n = 48, batch = 6, ldda = 48, i, b;
+    double *hA, *dA; magma_int_t *hipiv, *dipiv, *dinfo, hinfo[6]; double **dA_array; magma_int_t **dipiv_array;
+    magma_queue_t queue;
+    if (magma_init() != MAGMA_SUCCESS) return 2;
+    magma_queue_create(0, &queue);
+    hA = (double *)malloc(sizeof(double) * ldda * n * batch);
+    hipiv = (magma_int_t *)malloc(sizeof(magma_int_t) * n * batch);
+    for (i = 0; i < ldda * n * batch; ++i) hA[i] = (double)((i * 2654435761u) % 1000003u) / 1000003.0;
+    if (magma_malloc((void **)&dA, sizeof(double) * ldda * n * batch) != MAGMA_SUCCESS) return 3;
+    magma_malloc((void **)&dipiv, sizeof(magma_int_t) * n * batch);
+    magma_malloc((void **)&dinfo, sizeof(magma_int_t) * batch);
+    magma_malloc((void **)&dA_array, sizeof(double *) * batch);
+    magma_malloc((void **)&dipiv_array, sizeof(magma_int_t *) * batch);
+    magma_dsetmatrix(n, n * batch, hA, ldda, dA, ldda, queue);
+    magma_dset_pointer(dA_array, dA, ldda, 0, 0, ldda * n, batch, queue);
+    magma_iset_pointer(dipiv_array, dipiv, 1, 0, 0, n, batch, queue);
+    if (magma_dgetrf_batched(n, n, dA_array, ldda, dipiv_array, dinfo, batch, queue) != 0) return 4;
+    magma_queue_sync(queue);
+    magma_dgetmatrix(n, n * batch, dA, ldda, hA, ldda, queue);
+    magma_getvector(n * batch, sizeof(magma_int_t), dipiv, 1, hipiv, 1, queue);
+    magma_getvector(batch, sizeof(magma_int_t), dinfo, 1, hinfo, 1, queue);
+    for (b = 0; b < batch; ++b) {
+        if (hinfo[b] != 0) return 5;
+        for (i = 0; i < n; ++i) {
+            magma_int_t p = hipiv[b * n + i];
+            if (p < i + 1 || p > n) return 6;
+            printf("%d ", (int)p);
+        }
+        printf("\n");
+    }
+    for (i = 0; i < ldda * n * batch; ++i) printf("%.17g\n", hA[i]);
+    magma_free(dA); magma_free(dipiv); magma_free(dinfo); magma_free(dA_array); magma_free(dipiv_array);
+    magma_queue_destroy(queue);
+    magma_finalize();
+    return 0;
+}
+'''
+
+
+def test_c_program_links_and_runs(tmp_path, lib):
+    src = tmp_path / "tester.c"
+    src.write_text(C_PROG)
+    exe = tmp_path / "tester"
+    libdir = os.path.join(ROOT, "magma_b200", "lib")
+    cmd = ["gcc", "-O1", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-lmagma_b200", f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stderr[-1000:])
+    lines = r.stdout.strip().splitlines()
+    n, batch = 48, 6
+    ipiv = np.array([[int(t) for t in ln.split()] for ln in lines[:batch]], dtype=np.int32)
+    LU = np.array([float(t) for t in lines[batch:]]).reshape(batch, n, n)
+    idx = np.arange(n * n * batch, dtype=np.uint64)
+    A0 = (((idx * np.uint64(2654435761)) % np.uint64(2 ** 32)) % np.uint64(1000003)).astype(np.float64) / 1000003.0
+    A0 = A0.reshape(batch, n, n)
+    ref = A0.copy()
+    ipr, infr = oracle.getrf_batched(ref, n)
+    assert np.array_equal(ipiv, ipr)
+    assert np.array_equal(LU, ref)

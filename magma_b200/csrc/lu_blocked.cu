@@ -1091,6 +1091,19 @@ __device__ __forceinline__ void ll_mbar_wait(void *bar, unsigned parity)
         : "memory");
 }
 
+__device__ __forceinline__ void ll_mbar_expect_tx(void *bar, unsigned bytes)  // transaction bytes only, no arrival
+{
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void ll_bulk_load(void *smem_dst, const void *gsrc, unsigned bytes, void *bar)  // 1-D TMA copy
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
 template <int NW>
 struct LeftSmem {
     static constexpr int RING = (NW == 4) ? 3 : 4;  // chunks in the ring
@@ -1102,7 +1115,7 @@ struct LeftSmem {
     double Ls[32 * 33];                     // L_KK: read by the solve, refilled (cp.async) during the ring pass
     unsigned short rmap[NW][NW * 32];       // row i of the current order -> row in the order of panel K
     unsigned short src[NW * 32];            // row i of the current order -> original row (slab load)
-    unsigned long long full[RING], empty[RING], lsbar;
+    unsigned long long full[RING], empty[RING], lsbar, stbar;
     alignas(16) double ring[RING * 8 * LDR];  // L chunks, CTA-wide, rows in the order of their own panel; the staged
                                             // step permutations (NW x NW*32 shorts) live here during set-up
 };
@@ -1110,7 +1123,7 @@ struct LeftSmem {
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, NW == 16 ? 1 : (NW == 8 ? 2 : 4))
 left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__restrict__ sinv_g, int sinv_rows,
-                   int sinv_blocks, int J, int finish, int ahead, long batch, const int *__restrict__ index_list)
+                   int sinv_blocks, int J, int finish, int ahead, int use_bulk, long batch, const int *__restrict__ index_list)
 {
     // ahead: chunks in flight (1 .. RING-1); a ring slot is refilled RING - ahead chunks after its last use.
     // finish = 1: second visit of the slab that holds the LAST, narrower panel of a wide matrix
@@ -1166,6 +1179,7 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
     // cp.async completions, empty[] the threads that are done reading.
     constexpr int LDR = LeftSmem<NW>::LDR;
     const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const bool bulk_ok = vec_ok && ((m & 1) == 0) && (use_bulk != 0);  // 16-byte aligned columns of a multiple of 16 bytes
     auto issue = [&](int nrel) {  // nrel: chunk number counted from the first step
         const int K = kfirst + (nrel >> 2), ch = nrel & 3;
         const int slot_r = nrel % RING;
@@ -1175,7 +1189,18 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             const int rlo = 32 * (K + 1);                     // even
             double *dst = S.ring + (size_t)slot_r * 8 * LDR;
             const double *colbase = A + (size_t)(32 * K + 8 * ch) * ld;
-            if (rlo < m) {
+            if (rlo < m && bulk_ok && kbK == 32) {
+                // TMA: one bulk copy per column of the chunk, issued by one thread; the slot's barrier takes the bytes
+                // as a transaction count on top of the T plain arrivals below (LDGSTS needed up to four copies plus
+                // address arithmetic from every thread: 20% of the kernel's stall samples sat in this block)
+                if (tid == 0) {
+                    const unsigned bytes = (unsigned)(m - rlo) * 8u;
+                    ll_mbar_expect_tx(&S.full[slot_r], 8u * bytes);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        ll_bulk_load(dst + kk * LDR + rlo, colbase + (size_t)kk * ld + rlo, bytes, &S.full[slot_r]);
+                }
+            } else if (rlo < m) {
                 if (vec_ok) {
                     const int npairs = (m - rlo + 1) >> 1;
                     const unsigned magic = 0xFFFFFFFFu / (unsigned)npairs + 1u;  // u / npairs == umulhi(u, magic) for npairs > 1 (u * npairs < 2^32)
@@ -1225,6 +1250,7 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             ll_mbar_init(&S.empty[i], T);
         }
         ll_mbar_init(&S.lsbar, T);
+        ll_mbar_init(&S.stbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1238,7 +1264,23 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
     double acc[4][4][2];
 #pragma unroll
     for (int p0 = 0; p0 < 32; p0 += SCOLS) {
-        if (vec_ok) {
+        if (bulk_ok) {
+            // TMA: one bulk copy per slab column (columns outside [cb, nc) are not staged: their accumulators are
+            // never stored)
+            if (tid == 0) {
+                int ncopy = 0;
+                for (int cc = 0; cc < SCOLS; ++cc) ncopy += (p0 + cc >= cb && p0 + cc < nc) ? 1 : 0;
+                asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
+                                 (unsigned)__cvta_generic_to_shared(&S.stbar)),
+                             "r"((unsigned)ncopy * (unsigned)m * 8u)
+                             : "memory");
+                for (int cc = 0; cc < SCOLS; ++cc) {
+                    const int col = p0 + cc;
+                    if (col >= cb && col < nc) ll_bulk_load(S.ring + cc * LDR, A + (size_t)(c0 + col) * ld, (unsigned)m * 8u, &S.stbar);
+                }
+            }
+            ll_mbar_wait(&S.stbar, (unsigned)((p0 / SCOLS) & 1));
+        } else if (vec_ok) {
             const int npairs = (m + 1) >> 1;
             const unsigned magic = 0xFFFFFFFFu / (unsigned)npairs + 1u;
             for (int u = tid; u < SCOLS * npairs; u += T) {
@@ -1260,8 +1302,10 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
                 cp_async8(S.ring + cc * LDR + r, ok ? A + r + (size_t)(c0 + col) * ld : A, ok);
             }
         }
-        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
+        if (!bulk_ok) {
+            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+        }
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int row = 8 * (w + NW * a) + g;
@@ -1461,7 +1505,12 @@ magma_int_t launch_left_update(const Dims &d, double **dA, const unsigned short 
         if (ahead < 1) ahead = 1;
         if (ahead > LeftSmem<NW>::RING - 1) ahead = LeftSmem<NW>::RING - 1;
     }
-    left_update_kernel<NW><<<(unsigned)batch, NW * 32, smem, s>>>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, ahead, batch, il);
+    static int use_bulk = -1;
+    if (use_bulk < 0) {
+        const char *e = getenv("MB200_LL_BULK");  // 0: LDGSTS staging instead of TMA bulk copies (A/B runs)
+        use_bulk = e ? atoi(e) : 1;
+    }
+    left_update_kernel<NW><<<(unsigned)batch, NW * 32, smem, s>>>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, ahead, use_bulk, batch, il);
     count_launch();
     MB200_CHECK_LAUNCH("left_update_kernel");
     return 0;

@@ -356,6 +356,10 @@ int64_t magma_b200_launch_count(void);
  * 4 = blocked tier and getrs on the DFMA kernels only (no tensor pipe), 5 = no 64-wide pairing,
  * 6 = right-looking blocked driver everywhere, 7 = left-looking slab driver up to 512 rows (default: 448). */
 void magma_b200_set_tier(int tier);
+/* B200 tier boundaries, the same table the drivers dispatch on: which = 0 register tier (max(m,n) <=), 1 register-file
+ * tier (<=), 2 left-looking slab driver (rows <=), 3 single-launch shared-memory tier (<=; 0 = off).
+ * Counterpart of control/get_batched_crossover.cpp for this path. */
+magma_int_t magma_b200_get_dgetrf_batched_crossover(magma_int_t which);
 /* Self-test of the inline reciprocal of lu_fused.cu: mismatches against IEEE 1.0/x over n pseudo-random inputs (0 expected). */
 int64_t magma_b200_rcp_selftest(int64_t n, magma_queue_t queue);
 /* Largest max(m,n) routed to the single-launch shared-memory tier (lu_fused.cu), 0..128; 0 disables it (A/B runs). */

@@ -48,30 +48,38 @@ void magma_get_dgetrf_batched_nbparam(magma_int_t n, magma_int_t *nb, magma_int_
     // Reference: nb = 128, recnb = 32 for every n (control/get_batched_crossover.cpp:300-305).
     // Here the outer step IS the register panel width: 32 columns while the panel is <= 512 rows
     // tall, halving each time the height doubles; there is no inner recursion (recnb == nb).
-    int w = 32;
-    if (n > 512) w = 16;
-    if (n > 1024) w = 8;
-    if (n > 2048) w = 4;
-    if (n > 4096) w = 2;
-    if (n > 8192) w = 8;
+    // n stands for the panel height (square matrices: the first, tallest panel); the driver asks the same table
+    // with the rows that are left at each step
+    const int w = panel_width_for_rows(n);
     *nb = w;
     *recnb = w;
 }
 
 void magma_get_dgetrf_vbatched_nbparam(magma_int_t max_m, magma_int_t max_n, magma_int_t *nb, magma_int_t *recnb)
 {
-    magma_get_dgetrf_batched_nbparam(max_m > max_n ? max_m : max_n, nb, recnb);
+    (void)max_n;
+    magma_get_dgetrf_batched_nbparam(max_m, nb, recnb);  // the panel width follows the panel HEIGHT
 }
 
 magma_int_t magma_get_dgetrf_batched_ntcol(magma_int_t m, magma_int_t n)
 {
     // matrices per warp in the register tier (the reference's "ntcol" = matrices per CTA,
     // control/get_ntcol.cpp:197-210, is 1 for n >= 17 on anything newer than Volta)
-    const int k = m > n ? m : n;
-    if (k <= 8) return 4 * 4;   // 4 per warp x 4 warps per CTA
-    if (k <= 16) return 2 * 4;
-    if (k <= 32) return 1 * 4;
-    return 1;
+    const int per_warp = small_tier_matrices_per_warp(m, n);
+    return per_warp > 0 ? per_warp * 4 : 1;  // x 4 warps per CTA; above the register tier one matrix per CTA
+}
+
+// which: 0 register tier (max(m,n) <=), 1 register-file tier (<=), 2 left-looking slab driver (rows <=),
+// 3 single-launch shared-memory tier (<=, 0 = off)
+magma_int_t magma_b200_get_dgetrf_batched_crossover(magma_int_t which)
+{
+    switch (which) {
+        case 0: return XOVER_SMALL;
+        case 1: return XOVER_MID;
+        case 2: return XOVER_LEFT_ROWS;
+        case 3: return g_fused_max;
+        default: return -1;
+    }
 }
 
 magma_int_t magma_get_dtrsm_batched_stop_nb(magma_side_t side, magma_int_t m, magma_int_t n)
@@ -96,11 +104,11 @@ magma_int_t magma_dgetrf_batched(magma_int_t m, magma_int_t n, double **dA_array
     if (m == 0 || n == 0 || batchCount <= 0) return 0;
 
     const Dims d = uniform_dims(m, n, ldda);
-    cudaStream_t s = queue->stream;
+    cudaStream_t s = MB200_Q(queue)->stream;
     for (long off = 0; off < batchCount; off += MAX_CHUNK) {
         const long cnt = std::min<long>(MAX_CHUNK, batchCount - off);
         magma_int_t rc = -100;
-        if (m <= 32 && n <= 32 && g_tier != 2)
+        if (magma_get_dgetrf_batched_ntcol(m, n) > 1 && g_tier != 2)  // register tier
             rc = lu_small_launch(d, m, n, dA_array + off, ipiv_array + off, info_array + off, 0, nullptr, 0, cnt,
                                  nullptr, s);
         else if (m <= g_fused_max && n <= g_fused_max && g_tier != 2)
@@ -143,7 +151,7 @@ magma_int_t magma_dgetrf_batched_smallsq_noshfl(magma_int_t n, double **dA_array
     for (long off = 0; off < batchCount; off += MAX_CHUNK) {
         const long cnt = std::min<long>(MAX_CHUNK, batchCount - off);
         magma_int_t rc = lu_small_launch(d, n, n, dA_array + off, ipiv_array + off, info_array + off, 0, nullptr, 0,
-                                         cnt, nullptr, queue->stream);
+                                         cnt, nullptr, MB200_Q(queue)->stream);
         if (rc != 0) return rc;
     }
     return 0;
@@ -168,7 +176,7 @@ magma_int_t magma_dgesv_batched_small(magma_int_t n, magma_int_t nrhs, double **
     for (long off = 0; off < batchCount; off += MAX_CHUNK) {
         const long cnt = std::min<long>(MAX_CHUNK, batchCount - off);
         magma_int_t rc = lu_small_launch(d, n, n, dA_array + off, dipiv_array + off, dinfo_array + off, nrhs,
-                                         dB_array + off, lddb, cnt, nullptr, queue->stream);
+                                         dB_array + off, lddb, cnt, nullptr, MB200_Q(queue)->stream);
         if (rc != 0) return rc;
     }
     return 0;
@@ -192,7 +200,7 @@ magma_int_t magma_dgetrs_batched(magma_trans_t trans, magma_int_t n, magma_int_t
     for (long off = 0; off < batchCount; off += MAX_CHUNK) {
         const long cnt = std::min<long>(MAX_CHUNK, batchCount - off);
         magma_int_t rc = getrs_launch(trans, n, nrhs, dA_array + off, ldda, dipiv_array + off, dB_array + off, lddb,
-                                      cnt, queue->stream);
+                                      cnt, MB200_Q(queue)->stream);
         if (rc != 0) {
             magma_xerbla(__func__, -rc);
             return rc;
@@ -218,7 +226,7 @@ magma_int_t magma_dgetrf_nopiv_batched(magma_int_t m, magma_int_t n, double **dA
         return arginfo;
     }
     if (batchCount <= 0) return 0;
-    cudaStream_t s = queue->stream;
+    cudaStream_t s = MB200_Q(queue)->stream;
     cudaMemsetAsync(info_array, 0, sizeof(int) * (size_t)batchCount, s);  // src/zgetrf_nopiv_batched.cpp:85
     if (m == 0 || n == 0) return 0;
     if (m > 512) {
@@ -264,7 +272,7 @@ magma_int_t magma_dgetrs_nopiv_batched(magma_trans_t trans, magma_int_t n, magma
     for (long off = 0; off < batchCount; off += MAX_CHUNK) {
         const long cnt = std::min<long>(MAX_CHUNK, batchCount - off);
         const magma_int_t rc = getrs_launch(trans, n, nrhs, dA_array + off, ldda, nullptr, dB_array + off, lddb, cnt,
-                                            queue->stream);
+                                            MB200_Q(queue)->stream);
         if (rc != 0) {
             magma_xerbla(__func__, -rc);
             return rc;
@@ -311,7 +319,7 @@ magma_int_t magma_dgetri_outofplace_batched(magma_int_t n, double **dA_array, ma
         return info;
     }
     if (n == 0 || batchCount <= 0) return 0;
-    identity_launch(n, dinvA_array, lddia, batchCount, queue->stream);
+    identity_launch(n, dinvA_array, lddia, batchCount, MB200_Q(queue)->stream);
     return magma_dgetrs_batched(MagmaNoTrans, n, n, dA_array, ldda, dipiv_array, dinvA_array, lddia, batchCount, queue);
 }
 
@@ -362,7 +370,7 @@ static magma_int_t vbatched_run(magma_int_t *m, magma_int_t *n, int max_m, int m
                                 magma_int_t *ldda, magma_int_t **ipiv_array, magma_int_t *info_array, void *work,
                                 long batch, magma_queue_t queue, const int *known)
 {
-    cudaStream_t s = queue->stream;
+    cudaStream_t s = MB200_Q(queue)->stream;
     Dims d;
     d.m = max_m;
     d.n = max_n;
@@ -460,10 +468,10 @@ magma_int_t magma_dgetrf_vbatched(magma_int_t *m, magma_int_t *n, double **dA_ar
     }
     int *stats = (int *)scr;  // 16 ints, then the partition workspace
     void *work = scr + 64;
-    vbatched_stats_launch(m, n, ldda, batchCount, stats, queue->stream);
+    vbatched_stats_launch(m, n, ldda, batchCount, stats, MB200_Q(queue)->stream);
     int h[16];
-    cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, queue->stream);
-    cudaStreamSynchronize(queue->stream);
+    cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, MB200_Q(queue)->stream);
+    cudaStreamSynchronize(MB200_Q(queue)->stream);
     if (h[4] != 0) {
         const int arg = 8 - h[4];  // 1: m, 2: n, 4: ldda (src/zgetrf_vbatched.cpp:356-364 via the checker)
         magma_xerbla(__func__, arg);
@@ -471,7 +479,7 @@ magma_int_t magma_dgetrf_vbatched(magma_int_t *m, magma_int_t *n, double **dA_ar
     }
     const int max_m = h[0], max_n = h[1];
     if (max_m == 0 || max_n == 0 || h[6] == 0) {
-        cudaMemsetAsync(info_array, 0, sizeof(int) * (size_t)batchCount, queue->stream);
+        cudaMemsetAsync(info_array, 0, sizeof(int) * (size_t)batchCount, MB200_Q(queue)->stream);
         return 0;
     }
     // bin sizes as the partition kernel will produce them (classes above mid_max fall into the last bin)
@@ -485,7 +493,7 @@ magma_int_t magma_dgetrf_vbatched(magma_int_t *m, magma_int_t *n, double **dA_ar
     magma_int_t rc = vbatched_run(m, n, max_m, max_n, dA_array, ldda, ipiv_array, info_array, work, batchCount, queue,
                                   known);
     // the reference's driver returns after a queue sync (src/zgetrf_vbatched.cpp:392)
-    cudaStreamSynchronize(queue->stream);
+    cudaStreamSynchronize(MB200_Q(queue)->stream);
     return rc;
 }
 
@@ -496,7 +504,7 @@ void magma_dlaswp_rowserial_batched(magma_int_t n, double **dA_array, magma_int_
                                     magma_int_t k2, magma_int_t **ipiv_array, magma_int_t batchCount,
                                     magma_queue_t queue)
 {
-    laswp_rowserial_launch(n, dA_array, lda, k1, k2, ipiv_array, batchCount, queue->stream);
+    laswp_rowserial_launch(n, dA_array, lda, k1, k2, ipiv_array, batchCount, MB200_Q(queue)->stream);
 }
 
 void magmablas_dtrsm_batched(magma_side_t side, magma_uplo_t uplo, magma_trans_t transA, magma_diag_t diag,
@@ -521,7 +529,7 @@ void magmablas_dtrsm_batched(magma_side_t side, magma_uplo_t uplo, magma_trans_t
         magma_xerbla(__func__, -info);
         return;
     }
-    trsm_left_launch(uplo, transA, diag, m, n, alpha, dA_array, ldda, dB_array, lddb, batchCount, queue->stream);
+    trsm_left_launch(uplo, transA, diag, m, n, alpha, dA_array, ldda, dB_array, lddb, batchCount, MB200_Q(queue)->stream);
 }
 
 void magma_dgemm_batched_core(magma_trans_t transA, magma_trans_t transB, magma_int_t m, magma_int_t n,
@@ -535,41 +543,41 @@ void magma_dgemm_batched_core(magma_trans_t transA, magma_trans_t transB, magma_
         return;
     }
     gemm_nn_launch(m, n, k, alpha, dA_array, Ai, Aj, ldda, dB_array, Bi, Bj, lddb, beta, dC_array, Ci, Cj, lddc,
-                   batchCount, queue->stream);
+                   batchCount, MB200_Q(queue)->stream);
 }
 
 void magma_dset_pointer(double **output_array, double *input, magma_int_t lda, magma_int_t row, magma_int_t column,
                         magma_int_t batch_offset, magma_int_t batchCount, magma_queue_t queue)
 {
     set_pointer_launch((void **)output_array, (char *)input, sizeof(double), lda, row, column, batch_offset,
-                       batchCount, queue->stream);
+                       batchCount, MB200_Q(queue)->stream);
 }
 
 void magma_iset_pointer(magma_int_t **output_array, magma_int_t *input, magma_int_t lda, magma_int_t row,
                         magma_int_t column, magma_int_t batchSize, magma_int_t batchCount, magma_queue_t queue)
 {
     set_pointer_launch((void **)output_array, (char *)input, sizeof(magma_int_t), lda, row, column, batchSize,
-                       batchCount, queue->stream);
+                       batchCount, MB200_Q(queue)->stream);
 }
 
 void magma_ddisplace_pointers(double **output_array, double **input_array, magma_int_t lda, magma_int_t row,
                               magma_int_t column, magma_int_t batchCount, magma_queue_t queue)
 {
     displace_pointers_launch((void **)output_array, (void **)input_array, sizeof(double), lda, row, column,
-                             batchCount, queue->stream);
+                             batchCount, MB200_Q(queue)->stream);
 }
 
 void magma_idisplace_pointers(magma_int_t **output_array, magma_int_t **input_array, magma_int_t lda,
                               magma_int_t row, magma_int_t column, magma_int_t batchCount, magma_queue_t queue)
 {
     displace_pointers_launch((void **)output_array, (void **)input_array, sizeof(magma_int_t), lda, row, column,
-                             batchCount, queue->stream);
+                             batchCount, MB200_Q(queue)->stream);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Additions
 // ---------------------------------------------------------------------------------------------
-int64_t magma_b200_rcp_selftest(int64_t n, magma_queue_t queue) { return rcp_selftest_run((long)n, queue->stream); }
+int64_t magma_b200_rcp_selftest(int64_t n, magma_queue_t queue) { return rcp_selftest_run((long)n, MB200_Q(queue)->stream); }
 void magma_b200_set_fused_max(int n) { g_fused_max = n > 128 ? 128 : (n < 0 ? 0 : n); }
 void magma_b200_set_mid_max(int n) { g_mid_max = n >= 128 ? 128 : (n >= 96 ? 96 : (n >= 64 ? 64 : 32)); }
 
@@ -578,7 +586,7 @@ void magma_b200_dlarnv_uniform(magma_int_t *iseed, int64_t n, double *dx, magma_
     const unsigned long long A = 33952834046453ull, MASK = (1ull << 48) - 1ull;
     unsigned long long s = ((unsigned long long)(iseed[0] & 4095) << 36) | ((unsigned long long)(iseed[1] & 4095) << 24) |
                            ((unsigned long long)(iseed[2] & 4095) << 12) | (unsigned long long)(iseed[3] & 4095);
-    dlarnv_launch(s, n, dx, queue->stream);
+    dlarnv_launch(s, n, dx, MB200_Q(queue)->stream);
     // advance the host seed by n draws: s * A^n
     unsigned long long p = A, e = (unsigned long long)n;
     while (e) {
@@ -592,8 +600,8 @@ void magma_b200_dlarnv_uniform(magma_int_t *iseed, int64_t n, double *dx, magma_
     iseed[3] = (int)(s & 4095);
 }
 
-double magma_b200_fp64_peak_tflops(int kind, magma_queue_t queue) { return fp64_peak_run(kind, queue->stream); }
-double magma_b200_hbm_copy_gbs(size_t bytes, magma_queue_t queue) { return hbm_copy_run(bytes, queue->stream); }
+double magma_b200_fp64_peak_tflops(int kind, magma_queue_t queue) { return fp64_peak_run(kind, MB200_Q(queue)->stream); }
+double magma_b200_hbm_copy_gbs(size_t bytes, magma_queue_t queue) { return hbm_copy_run(bytes, MB200_Q(queue)->stream); }
 
 magma_int_t magma_b200_dgetrf_batched_mgpu(magma_int_t ngpu, magma_int_t m, magma_int_t n, double ***dA_array,
                                            magma_int_t ldda, magma_int_t ***ipiv_array, magma_int_t **info_array,
@@ -603,7 +611,7 @@ magma_int_t magma_b200_dgetrf_batched_mgpu(magma_int_t ngpu, magma_int_t m, magm
     cudaGetDevice(&prev);
     magma_int_t rc = 0;
     for (int g = 0; g < ngpu && rc == 0; ++g) {
-        cudaSetDevice(queues[g]->device);
+        cudaSetDevice(MB200_Q(queues[g])->device);
         rc = magma_dgetrf_batched(m, n, dA_array[g], ldda, ipiv_array[g], info_array[g], batchCount[g], queues[g]);
     }
     cudaSetDevice(prev);
@@ -619,7 +627,7 @@ magma_int_t magma_b200_dgesv_batched_mgpu(magma_int_t ngpu, magma_int_t n, magma
     cudaGetDevice(&prev);
     magma_int_t rc = 0;
     for (int g = 0; g < ngpu && rc == 0; ++g) {
-        cudaSetDevice(queues[g]->device);
+        cudaSetDevice(MB200_Q(queues[g])->device);
         rc = magma_dgesv_batched(n, nrhs, dA_array[g], ldda, dipiv_array[g], dB_array[g], lddb, dinfo_array[g],
                                  batchCount[g], queues[g]);
     }
@@ -630,12 +638,18 @@ magma_int_t magma_b200_dgesv_batched_mgpu(magma_int_t ngpu, magma_int_t n, magma
 // ---------------------------------------------------------------------------------------------
 // Host-buffer front ends: chunked, double-buffered H2D -> compute -> D2H.
 // ---------------------------------------------------------------------------------------------
-static void ensure_aux(magma_queue_t q)
+static void ensure_aux(magma_queue_t queue)
 {
+    auto *q = MB200_Q(queue);
     if (q->aux_ready) return;
+    // the auxiliary streams and events belong to the queue's device, whatever device is current
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (prev != q->device) cudaSetDevice(q->device);
     for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&q->aux_stream[i], cudaStreamNonBlocking);
     for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&q->aux_event[i], cudaEventDisableTiming);
     q->aux_ready = true;
+    if (prev != q->device) cudaSetDevice(prev);
 }
 
 static magma_int_t host_pipeline(bool solve, int m, int n, int nrhs, double *hA, int lda, int *hipiv, double *hB,
@@ -659,12 +673,12 @@ static magma_int_t host_pipeline(bool solve, int m, int n, int nrhs, double *hA,
         magma_xerbla(solve ? "magma_b200_dgesv_batched_host" : "magma_b200_dgetrf_batched_host", -MAGMA_ERR_DEVICE_ALLOC);
         return MAGMA_ERR_DEVICE_ALLOC;
     }
-    cudaStream_t sc = queue->stream;
-    cudaStream_t sh = queue->aux_stream[0];  // H2D
-    cudaStream_t sd = queue->aux_stream[1];  // D2H
-    cudaEvent_t *ev_in = queue->aux_event;        // [2] H2D done
-    cudaEvent_t *ev_done = queue->aux_event + 2;  // [2] compute done
-    cudaEvent_t *ev_out = queue->aux_event + 4;   // [2] D2H done (buffer free)
+    cudaStream_t sc = MB200_Q(queue)->stream;
+    cudaStream_t sh = MB200_Q(queue)->aux_stream[0];  // H2D
+    cudaStream_t sd = MB200_Q(queue)->aux_stream[1];  // D2H
+    cudaEvent_t *ev_in = MB200_Q(queue)->aux_event;        // [2] H2D done
+    cudaEvent_t *ev_done = MB200_Q(queue)->aux_event + 2;  // [2] compute done
+    cudaEvent_t *ev_out = MB200_Q(queue)->aux_event + 4;   // [2] D2H done (buffer free)
     magma_int_t rc = 0;
     long it = 0;
     for (long off = 0; off < batch; off += chunk, ++it) {

@@ -10,7 +10,19 @@
 
 // The opaque queue (replaces control/magma_internal.h:90-211). No cuBLAS/cuSPARSE handles and no
 // 3x65534 pointer scratch: nothing on this path calls a vendor BLAS or displaces pointer arrays.
+// Two deployment modes:
+//   standalone (default): this library owns the queue type below and exports the minimal runtime around it;
+//   interpose (-DMB200_INTERPOSE): the queue belongs to a real libmagma and stays opaque -- stream and device are read
+//     through ITS magma_queue_get_cuda_stream / magma_queue_get_device (interface_cuda/interface.cpp:798,815), never by
+//     struct layout, and this library's per-queue state (scratch, auxiliary streams) lives in a side table keyed by
+//     the handle. runtime.cu's entry points are compiled out; only the batched-LU symbols are defined.
+#ifdef MB200_INTERPOSE
+struct magma_queue;  // opaque: owned by the real libmagma
+namespace mb200 {
+struct QState {
+#else
 struct magma_queue {
+#endif
     magma_device_t device;
     cudaStream_t stream;
     bool own_stream;
@@ -24,12 +36,43 @@ struct magma_queue {
     cudaEvent_t aux_event[8];
     bool aux_ready;
 };
+#ifdef MB200_INTERPOSE
+QState *qstate(magma_queue_t q);  // finds or creates the entry; refreshes stream and device from the real queue
+}  // namespace mb200
+#define MB200_Q(q) (mb200::qstate(q))
+#else
+#define MB200_Q(q) (q)
+#endif
 
 namespace mb200 {
 
 extern std::atomic<int64_t> g_launches;
 extern int g_tier;  // 0 auto, 1 force small/register tier, 2 force blocked tier
 extern int g_small_rows;  // register tier: rows per lane, 0 = tuned default
+
+// ---- B200 tuning table: the ONE place tier boundaries and panel widths are written down. The drivers below and the
+// reference-named getters (magma_get_dgetrf_batched_nbparam / _ntcol, magma_b200_get_dgetrf_batched_crossover) all
+// read it (control/get_batched_crossover.cpp:300-305, control/get_ntcol.cpp:197-210 are its reference counterparts).
+constexpr int XOVER_SMALL = 32;       // max(m,n) <= 32: register tier, one launch (lu_small*.cu)
+constexpr int XOVER_MID = 44;         // 33..44: register-file tier (lu_mid.cu); above: left-looking slab driver
+constexpr int XOVER_LEFT_ROWS = 512;  // at most 512 rows: left-looking slab driver; more: right-looking driver
+// width of the register panel for a panel `rows` tall: 32 columns while one thread per row fits a CTA (512 rows),
+// halving each time the height doubles; above 8192 rows the global-memory panel (8 columns)
+inline int panel_width_for_rows(int rows)
+{
+    if (rows <= 512) return 32;
+    if (rows <= 1024) return 16;
+    if (rows <= 2048) return 8;
+    if (rows <= 4096) return 4;
+    if (rows <= 8192) return 2;
+    return 8;
+}
+// matrices per warp in the register tier
+inline int small_tier_matrices_per_warp(int m, int n)
+{
+    const int k = m > n ? m : n;
+    return k <= 8 ? 4 : (k <= 16 ? 2 : (k <= XOVER_SMALL ? 1 : 0));
+}
 
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

@@ -139,7 +139,7 @@ magma_int_t panel_lu_offset(const char *func, int m, int n, double **dA_array, i
                             int *info_array, int gbstep, long batch, magma_queue_t queue)
 {
     if (m == 0 || n == 0 || batch <= 0) return 0;
-    cudaStream_t s = queue->stream;
+    cudaStream_t s = MB200_Q(queue)->stream;
     const size_t bytes = (size_t)batch * (sizeof(double *) + sizeof(int *) + sizeof(int));
     char *scr = (char *)queue_dscratch(queue, bytes, 0);
     if (!scr) {
@@ -234,7 +234,7 @@ void magma_dlaswp_rowparallel_batched(magma_int_t n, double **input_array, magma
     const long per = 0x7fffffffL / groups;
     for (long off = 0; off < batchCount; off += per) {
         const long cnt = batchCount - off < per ? batchCount - off : per;
-        laswp_rowparallel_kernel<<<(unsigned)(cnt * groups), threads, 0, queue->stream>>>(
+        laswp_rowparallel_kernel<<<(unsigned)(cnt * groups), threads, 0, MB200_Q(queue)->stream>>>(
             n, input_array + off, input_i, input_j, ldi, output_array + off, output_i, output_j, ldo, height,
             pivinfo_array + off, groups);
         count_launch();
@@ -266,7 +266,7 @@ void magmablas_dtrsv_batched(magma_uplo_t uplo, magma_trans_t transA, magma_diag
     const int t = (transA == MagmaNoTrans) ? MagmaNoTrans : MagmaTrans;
     for (long off = 0; off < batchCount; off += 0x7fffffffL) {
         const long cnt = batchCount - off < 0x7fffffffL ? batchCount - off : 0x7fffffffL;
-        trsv_kernel<<<(unsigned)cnt, TV_THREADS, smem, queue->stream>>>(uplo, t, diag, n, dA_array + off, ldda, dB_array + off,
+        trsv_kernel<<<(unsigned)cnt, TV_THREADS, smem, MB200_Q(queue)->stream>>>(uplo, t, diag, n, dA_array + off, ldda, dB_array + off,
                                                                        incb);
         count_launch();
         MB200_CHECK_LAUNCH_VOID("trsv_kernel");

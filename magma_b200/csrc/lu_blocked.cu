@@ -1112,7 +1112,7 @@ struct LeftSmem {
     double Un[32 * LL_LDU];                 // -U(K, J): written by the solve of step K (between the step's two
                                             // barriers), read by its ring pass; every warp is past that pass when
                                             // the next solve starts, so one buffer is enough
-    double Ls[32 * 33];                     // L_KK: read by the solve, refilled (cp.async) during the ring pass
+    alignas(16) double Ls[32 * 33];         // L_KK, column-major [k*32 + i]: read by the solve, refilled (TMA / cp.async) during the ring pass
     unsigned short rmap[NW][NW * 32];       // row i of the current order -> row in the order of panel K
     unsigned short src[NW * 32];            // row i of the current order -> original row (slab load)
     unsigned long long full[RING], empty[RING], lsbar, stbar;
@@ -1193,12 +1193,11 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
                 // TMA: one bulk copy per column of the chunk, issued by one thread; the slot's barrier takes the bytes
                 // as a transaction count on top of the T plain arrivals below (LDGSTS needed up to four copies plus
                 // address arithmetic from every thread: 20% of the kernel's stall samples sat in this block)
-                if (tid == 0) {
+                // (one copy per LANE: issued from a loop on one thread, the copies of a step cost that warp ~2k cycles)
+                if (tid < 8) {
                     const unsigned bytes = (unsigned)(m - rlo) * 8u;
-                    ll_mbar_expect_tx(&S.full[slot_r], 8u * bytes);
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                        ll_bulk_load(dst + kk * LDR + rlo, colbase + (size_t)kk * ld + rlo, bytes, &S.full[slot_r]);
+                    if (tid == 0) ll_mbar_expect_tx(&S.full[slot_r], 8u * bytes);
+                    ll_bulk_load(dst + tid * LDR + rlo, colbase + (size_t)tid * ld + rlo, bytes, &S.full[slot_r]);
                 }
             } else if (rlo < m) {
                 if (vec_ok) {
@@ -1237,10 +1236,17 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
     auto stage_lkk = [&](int K) {  // L_KK -> Ls, zero outside the panel width
         const int kbK = (kend - 32 * K) < 32 ? (kend - 32 * K) : 32;
         const double *LKK = A + (size_t)(32 * K) + (size_t)(32 * K) * ld;
-        for (int idx = tid; idx < 1024; idx += T) {
-            const int i = idx & 31, k = idx >> 5;
-            const bool ok = (i < kbK && k < kbK);
-            cp_async8(&S.Ls[i * 33 + k], ok ? LKK + i + (size_t)k * ld : A, ok);
+        if (bulk_ok && (use_bulk & 2) && kbK == 32) {  // TMA: 32 columns of 256 bytes
+            if (tid < 32) {
+                if (tid == 0) ll_mbar_expect_tx(&S.lsbar, 32u * 256u);
+                ll_bulk_load(&S.Ls[tid * 32], LKK + (size_t)tid * ld, 256u, &S.lsbar);
+            }
+        } else {
+            for (int idx = tid; idx < 1024; idx += T) {
+                const int i = idx & 31, k = idx >> 5;
+                const bool ok = (i < kbK && k < kbK);
+                cp_async8(&S.Ls[k * 32 + i], ok ? LKK + i + (size_t)k * ld : A, ok);
+            }
         }
         ll_mbar_arrive_cp_async(&S.lsbar);
     };
@@ -1267,17 +1273,17 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
         if (bulk_ok) {
             // TMA: one bulk copy per slab column (columns outside [cb, nc) are not staged: their accumulators are
             // never stored)
-            if (tid == 0) {
-                int ncopy = 0;
-                for (int cc = 0; cc < SCOLS; ++cc) ncopy += (p0 + cc >= cb && p0 + cc < nc) ? 1 : 0;
-                asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
-                                 (unsigned)__cvta_generic_to_shared(&S.stbar)),
-                             "r"((unsigned)ncopy * (unsigned)m * 8u)
-                             : "memory");
-                for (int cc = 0; cc < SCOLS; ++cc) {
-                    const int col = p0 + cc;
-                    if (col >= cb && col < nc) ll_bulk_load(S.ring + cc * LDR, A + (size_t)(c0 + col) * ld, (unsigned)m * 8u, &S.stbar);
+            if (tid < SCOLS) {
+                if (tid == 0) {
+                    int ncopy = 0;
+                    for (int cc = 0; cc < SCOLS; ++cc) ncopy += (p0 + cc >= cb && p0 + cc < nc) ? 1 : 0;
+                    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
+                                     (unsigned)__cvta_generic_to_shared(&S.stbar)),
+                                 "r"((unsigned)ncopy * (unsigned)m * 8u)
+                                 : "memory");
                 }
+                const int col = p0 + tid;
+                if (col >= cb && col < nc) ll_bulk_load(S.ring + tid * LDR, A + (size_t)(c0 + col) * ld, (unsigned)m * 8u, &S.stbar);
             }
             ll_mbar_wait(&S.stbar, (unsigned)((p0 / SCOLS) & 1));
         } else if (vec_ok) {
@@ -1363,7 +1369,7 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
                     for (int sblk = 0; sblk < 4; ++sblk) {
                         if (8 * sblk + 7 > k) {  // static: this row group still has rows below k
                             const int i = g + 8 * sblk;
-                            const double l = Lk[i * 33 + k];
+                            const double l = Lk[k * 32 + i];
                             if (i > k) x[sblk] = fma(-l, u, x[sblk]);
                         }
                     }
@@ -1392,7 +1398,7 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
                 for (int i8 = 0; i8 < 8; ++i8) {
                     if (4 * i8 + 3 > k) {
                         const int i = rg + 4 * i8;
-                        const double l = Lk[i * 33 + k];
+                        const double l = Lk[k * 32 + i];
                         if (i > k) x[i8] = fma(-l, u, x[i8]);
                     }
                 }
@@ -1508,7 +1514,7 @@ magma_int_t launch_left_update(const Dims &d, double **dA, const unsigned short 
     static int use_bulk = -1;
     if (use_bulk < 0) {
         const char *e = getenv("MB200_LL_BULK");  // 0: LDGSTS staging instead of TMA bulk copies (A/B runs)
-        use_bulk = e ? atoi(e) : 1;
+        use_bulk = e ? atoi(e) : 1;  // bit 0: L chunks and slab (n = 512: 30.8 -> 27.2 ms), bit 1: L_KK too (32 copies of 256 B: 28.7 ms, off)
     }
     left_update_kernel<NW><<<(unsigned)batch, NW * 32, smem, s>>>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, ahead, use_bulk, batch, il);
     count_launch();
@@ -1803,11 +1809,11 @@ magma_int_t lu_blocked_launch(const Dims &d, int max_m, int max_n, double **dA, 
     PivRec *recs = reinterpret_cast<PivRec *>(workspace);
     const int max_mn = max_m < max_n ? max_m : max_n;  // upper bound of min(m_b, n_b)
     // tiers 4 (DFMA only), 5 (no pairing), 6 (right-looking) keep the right-looking flow for A/B runs
-    if (perm_workspace && max_n > 32 && max_m <= 512 && g_tier != 4 && g_tier != 5 &&
+    if (perm_workspace && max_n > 32 && max_m <= XOVER_LEFT_ROWS && g_tier != 4 && g_tier != 5 &&
         g_tier != 6)
         return run_left_looking(d, max_m, max_n, dA, dipiv, dinfo, recs, reinterpret_cast<unsigned short *>(perm_workspace),
                                 batch, index_list, s, 0);
-    const bool defer_left = (max_m <= 512);             // every step is 32 wide
+    const bool defer_left = (max_m <= XOVER_LEFT_ROWS);             // every step is 32 wide
     int pair_end_block = 0;                              // column blocks < this were factored in 64-wide pairs
     int j = 0;
     while (j < max_mn) {
@@ -1824,12 +1830,13 @@ magma_int_t lu_blocked_launch(const Dims &d, int max_m, int max_n, double **dA, 
             pair_end_block += 2;
             continue;
         }
-        if (mp <= 512)       { w = 32; rc = run_step<1, 32>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left); }
-        else if (mp <= 1024) { w = 16; rc = run_step<2, 16>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left); }
-        else if (mp <= 2048) { w = 8;  rc = run_step<4, 8>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left); }
-        else if (mp <= 4096) { w = 4;  rc = run_step<8, 4>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left); }
-        else if (mp <= 8192) { w = 2;  rc = run_step<16, 2>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left); }
-        else                 { w = 8;  rc = run_step<1, 8>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, true, defer_left); }
+        w = panel_width_for_rows(mp);  // the tuning table (common.cuh), also behind magma_get_dgetrf_batched_nbparam
+        if (mp > 8192)    rc = run_step<1, 8>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, true, defer_left);
+        else if (w == 32) rc = run_step<1, 32>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left);
+        else if (w == 16) rc = run_step<2, 16>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left);
+        else if (w == 8)  rc = run_step<4, 8>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left);
+        else if (w == 4)  rc = run_step<8, 4>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left);
+        else              rc = run_step<16, 2>(d, max_m, max_n, dA, dipiv, dinfo, recs, j, batch, index_list, s, false, defer_left);
         if (rc != 0) return rc;
         j += w;
     }

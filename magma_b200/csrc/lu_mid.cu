@@ -399,7 +399,7 @@ magma_int_t lu_mid_launch(const Dims &d, int max_m, int max_n, double **dA, int 
         // per SM and 4-warp slab updates beat one pivot chain per matrix. magma_b200_set_small_rows(7) keeps this
         // tier up to 128 (A/B runs, tests).
         const int mx = max_m > max_n ? max_m : max_n;
-        if (mx > 44 && g_small_rows != 7 && g_small_rows != 8) return -100;
+        if (mx > XOVER_MID && g_small_rows != 7 && g_small_rows != 8) return -100;
     }
     if (g_small_rows == 8) {  // the single-phase 16-warp kernel (A/B runs)
         if (max_m <= 64 && max_n <= 64) return launch_mid<2, 8, 1, 3>(d, dA, dipiv, dinfo, batch, index_list, s);

@@ -12,8 +12,28 @@ std::atomic<int64_t> g_launches{0};
 int g_tier = 0;
 static std::atomic<int> g_init_count{0};
 
-void *queue_dscratch(magma_queue_t q, size_t bytes, int slot)
+#ifdef MB200_INTERPOSE
+}  // namespace mb200
+#include <mutex>
+#include <unordered_map>
+namespace mb200 {
+QState *qstate(magma_queue_t q)
 {
+    static std::mutex mu;
+    static std::unordered_map<void *, QState *> table;
+    std::lock_guard<std::mutex> lock(mu);
+    QState *&st = table[(void *)q];
+    if (!st) st = (QState *)calloc(1, sizeof(QState));
+    // the handle may have been destroyed and re-created by its owner: always ask the real library
+    st->stream = (cudaStream_t)magma_queue_get_cuda_stream(q);
+    st->device = magma_queue_get_device(q);
+    return st;
+}
+#endif
+
+void *queue_dscratch(magma_queue_t queue, size_t bytes, int slot)
+{
+    auto *q = MB200_Q(queue);
     if (q->dscratch_bytes[slot] < bytes) {
         if (q->dscratch[slot]) {
             cudaStreamSynchronize(q->stream);
@@ -31,8 +51,9 @@ void *queue_dscratch(magma_queue_t q, size_t bytes, int slot)
     return q->dscratch[slot];
 }
 
-void *queue_hscratch(magma_queue_t q, size_t bytes)
+void *queue_hscratch(magma_queue_t queue, size_t bytes)
 {
+    auto *q = MB200_Q(queue);
     if (q->hscratch_bytes < bytes) {
         if (q->hscratch) cudaFreeHost(q->hscratch);
         q->hscratch = nullptr;
@@ -49,6 +70,7 @@ void *queue_hscratch(magma_queue_t q, size_t bytes)
 
 using namespace mb200;
 
+#ifndef MB200_INTERPOSE  // interpose mode: everything below is the real libmagma's
 extern "C" {
 
 // ---------------------------------------------------------------------------------------------
@@ -423,8 +445,11 @@ magma_int_t *magma_ioffset_2d(magma_int_t *A, magma_int_t lda, magma_int_t i, ma
     return A + (i - 1) + (ptrdiff_t)(j - 1) * lda;
 }
 
+}  // extern "C"
+#endif  // !MB200_INTERPOSE
+
+extern "C" {
 int64_t magma_b200_launch_count(void) { return g_launches.load(); }
 void magma_b200_set_tier(int tier) { g_tier = tier; }
 void magma_b200_set_small_rows(int rows) { g_small_rows = rows; }
-
 }  // extern "C"

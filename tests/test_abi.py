@@ -96,6 +96,25 @@ def test_offset_helpers_and_tuning(lib):
     assert batched.magma_get_dgetrf_batched_nbparam(1000) == (16, 16)
     assert lib.magma_get_dgetrf_batched_ntcol(16, 16) == 8
     assert lib.magma_get_dtrsm_batched_stop_nb(141, 100, 100) == 32
+    # the getters and the drivers read ONE table (csrc/common.cuh): monotone panel widths, tier boundaries
+    widths = [batched.magma_get_dgetrf_batched_nbparam(r)[0] for r in (1, 512, 513, 1024, 1025, 2048, 4096, 4097, 8192)]
+    assert widths == [32, 32, 16, 16, 8, 8, 4, 2, 2]
+    assert all(a >= b for a, b in zip(widths, widths[1:]))
+    assert [lib.magma_b200_get_dgetrf_batched_crossover(k) for k in (0, 1, 2)] == [32, 44, 512]
+    assert lib.magma_get_dgetrf_batched_ntcol(32, 32) == 4 and lib.magma_get_dgetrf_batched_ntcol(33, 33) == 1
+    assert lib.magma_get_dgetrf_batched_ntcol(8, 8) == 16
+
+
+def test_drop_in_headers_compile(tmp_path):
+    """`#include "magma_v2.h"` (and the batched sub-headers) keep working for a caller that switches libraries."""
+    import os
+    import subprocess
+    inc = os.path.join(os.path.dirname(_lib.HERE), "include")
+    for hdr in ("magma_v2.h", "magma_batched.h", "magma_dbatched.h"):
+        src = tmp_path / (hdr.replace(".", "_") + ".c")
+        src.write_text(f'#include "{hdr}"\nint f(void) {{ return (int)MagmaNoTrans + (int)sizeof(magma_queue_t); }}\n')
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
 
 
 def test_init_fails_loudly_without_gpu(lib, capfd):

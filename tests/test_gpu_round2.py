@@ -391,6 +391,33 @@ def test_against_reference_gpu(gpu_queue, tmp_path, n, batch, nrhs):
     assert np.max(np.abs(LU - ref["LU"])) <= 1e-9 * scale
 
 
+INTERPOSE_SO = os.path.join(ROOT, "magma_b200", "lib", "libmagma_b200_interpose.so")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_SO) and os.path.exists(INTERPOSE_SO)),
+                    reason="needs oracle/_ref/libmagma_ref.so and lib/libmagma_b200_interpose.so")
+@pytest.mark.parametrize("n,batch,nrhs", [(16, 500, 1), (32, 300, 0), (100, 20, 0), (300, 4, 3)])
+def test_interpose_mode(tmp_path, n, batch, nrhs):
+    """INTEGRATION.md mode 2: our batched-LU entry points on a queue that belongs to a real libmagma (here the compiled
+    reference), whose struct layout this library never touches. Results must equal the oracle bit for bit."""
+    out = tmp_path / "ip.npz"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "interpose_run.py"), str(n), str(batch), str(nrhs), str(out)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = np.load(out)
+    A0, seed = oracle.random_batch(batch, n, n)
+    if nrhs:
+        B0, _ = oracle.random_batch(batch, n, nrhs, iseed=seed)
+        Ar, Br = A0.copy(), B0.copy()
+        ipr, infr = oracle.gesv_batched(Ar, Br, n)
+        assert np.array_equal(got["X"], Br)
+    else:
+        Ar = A0.copy()
+        ipr, infr = oracle.getrf_batched(Ar, n)
+    assert np.array_equal(got["ipiv"], ipr) and np.array_equal(got["info"], infr)
+    assert np.array_equal(got["LU"], Ar)
+
+
 # ---- a C program linked against the library -----------------------------------------------------------------------------------
 
 C_PROG = r'''

@@ -131,22 +131,6 @@ __device__ __forceinline__ void f_sts8_if(bool p, unsigned a, int v)
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.u8 [%1], %2;\n\t}" ::"r"((unsigned)p), "r"(a), "r"(v) : "memory");
 }
 
-// 1/x for normal x with |x| in [2^-1000, 2^1000]: the instruction sequence nvcc emits for the fast path of an IEEE
-// double division 1.0/x (MUFU.RCP64H seed whose low word is hi(x) + 0x300402, two Newton steps), without the
-// per-lane range test and slow-path call -- the caller checks the range on the (warp-uniform) pivot exponent.
-// magma_b200_rcp_selftest compares it bit for bit with 1.0/x on the device.
-__device__ __forceinline__ double f_rcp_fast(double x)
-{
-    double y0;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
-    const double y = __hiloint2double(__double2hiint(y0), __double2hiint(x) + 0x300402);
-    double e = fma(-x, y, 1.0);
-    e = fma(e, e, e);
-    const double y1 = fma(y, e, y);
-    const double e2 = fma(-x, y1, 1.0);
-    return fma(y1, e2, y1);
-}
-
 // Exact pivot choice for the cases the fast path hands over (several rows share the largest high word, or the
 // column's high words are all zero): first maximum of |x| over every active row of the warp, ties to the smaller
 // logical position. Returns winner lane | slot << 8. Out of line: it runs on structured inputs only.
@@ -225,7 +209,7 @@ __device__ __forceinline__ void panel_chain(FusedSmem &S, const unsigned vbase, 
                 cv = f_sel(hit, a[k][i], cv);
                 lp = hit ? pos[k] : lp;
             }
-            const double rinv = f_rcp_fast(cv);  // this lane's candidate reciprocal, in flight while the vote runs
+            const double rinv = rcp_fast_f64(cv);  // this lane's candidate reciprocal, in flight while the vote runs
             asm volatile("" ::"d"(rinv));        // keep it ahead of the vote (ptxas sank it behind the slot switch)
             const unsigned tot = __reduce_add_sync(FULL, code);
             int wl, K;
@@ -680,7 +664,7 @@ __global__ void rcp_selftest_kernel(long n, unsigned long long seed, unsigned lo
     const unsigned long long ex = 1023ull - 990ull + ((z >> 52) & 0x7FFull) % 1981ull;
     const unsigned long long bits = ((z >> 63) << 63) | (ex << 52) | mant;
     const double x = __longlong_as_double((long long)bits);
-    const double a = f_rcp_fast(x), b = 1.0 / x;
+    const double a = rcp_fast_f64(x), b = 1.0 / x;
     if (__double_as_longlong(a) != __double_as_longlong(b)) atomicAdd(bad, 1ull);
 }
 

@@ -301,6 +301,21 @@ def main():
 
     # ---- e2e: host buffers through the C ABI (pinned), copies inside the timed region ---------
     e2e_steps = max(1, min(K, 5))
+    # pinned staging on the NUMA node next to this rank's GPU: first-touch placement follows the CPUs the thread may
+    # run on, so the rank pins itself to the GPU's local CPU set (NVML) while it allocates and while it drives copies
+    numa = {"cpus_bound": None}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            numa["cpus_bound"] = len(cpus)
+    except Exception as ex:  # noqa: BLE001
+        numa["error"] = str(ex)[:120]
     hA = torch.empty((batch, n, n), dtype=torch.float64).pin_memory()
     hB = torch.empty((batch, nrhs, n), dtype=torch.float64).pin_memory()
     hip = torch.empty((batch, n), dtype=torch.int32).pin_memory()
@@ -354,7 +369,7 @@ def main():
            "d2h_bytes_per_step": ((n * n + n * nrhs) * 8 + n * 4 + 4) * batch,
            "ms_per_step": 1e3 * sum(e2e_t) / len(e2e_t),
            "pcie_GBs_per_rank": ((n * n + n * nrhs) * 16 + n * 4 + 4) * batch / (sum(e2e_t) / len(e2e_t)) / 1e9,
-           "copy_only_ms": 1e3 * min(copy_t),
+           "copy_only_ms": 1e3 * min(copy_t), "numa": numa,
            "copy_only_note": "same bytes both ways on two streams with no kernel: the host-side ceiling at this rank count",
            "call": "magma_b200_dgesv_batched_host (pinned host A,B in; LU,X,ipiv,info out)"}
     del hA, hB, hA0, hB0, hip, hinfo

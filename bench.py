@@ -304,6 +304,7 @@ def main():
     # pinned staging on the NUMA node next to this rank's GPU: first-touch placement follows the CPUs the thread may
     # run on, so the rank pins itself to the GPU's local CPU set (NVML) while it allocates and while it drives copies
     numa = {"cpus_bound": None}
+    affinity0 = os.sched_getaffinity(0)
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -373,6 +374,7 @@ def main():
            "copy_only_note": "same bytes both ways on two streams with no kernel: the host-side ceiling at this rank count",
            "call": "magma_b200_dgesv_batched_host (pinned host A,B in; LU,X,ipiv,info out)"}
     del hA, hB, hA0, hB0, hip, hinfo
+    os.sched_setaffinity(0, affinity0)  # the CPU baseline below may use every core again
 
     # ---- peaks for the compute-bound rows ------------------------------------------------------
     peaks = {"hbm_gbs": hbm_peak, "hbm_source": peak_src,

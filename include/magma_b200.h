@@ -268,6 +268,22 @@ magma_int_t magma_dgesv_batched_small(magma_int_t n, magma_int_t nrhs, double **
 void magma_dlaswp_rowserial_batched(magma_int_t n, double **dA_array, magma_int_t lda, magma_int_t k1,
                                     magma_int_t k2, magma_int_t **ipiv_array, magma_int_t batchCount,
                                     magma_queue_t queue);
+/* Solve with a random butterfly transformation instead of pivoting: A <- U^T A V, B <- U^T B, LU without pivoting,
+ * triangular solves, X <- V Y. U, V: two-level butterflies of 2n scalars each, drawn with rand() as the reference does
+ * when gen = MagmaTrue.   src/zgesv_rbt_batched.cpp:81-166, src/zgerbt_batched.cpp:118-181,
+ * magmablas/zgerbt_func_batched.cu:57-210 */
+magma_int_t magma_dgesv_rbt_batched(magma_int_t n, magma_int_t nrhs, double **dA_array, magma_int_t ldda,
+                                    double **dB_array, magma_int_t lddb, magma_int_t *dinfo_array, magma_int_t batchCount,
+                                    magma_queue_t queue);
+magma_int_t magma_dgerbt_batched(magma_bool_t gen, magma_int_t n, magma_int_t nrhs, double **dA_array, magma_int_t ldda,
+                                 double **dB_array, magma_int_t lddb, double *U, double *V, magma_int_t *info,
+                                 magma_int_t batchCount, magma_queue_t queue);
+void magmablas_dprbt_batched(magma_int_t n, double **dA_array, magma_int_t ldda, double *du, double *dv,
+                             magma_int_t batchCount, magma_queue_t queue);
+void magmablas_dprbt_mv_batched(magma_int_t n, magma_int_t nrhs, double *dv, double **db_array, magma_int_t lddb,
+                                magma_int_t batchCount, magma_queue_t queue);
+void magmablas_dprbt_mtv_batched(magma_int_t n, magma_int_t nrhs, double *du, double **db_array, magma_int_t lddb,
+                                 magma_int_t batchCount, magma_queue_t queue);
 /* Panel-level entry points of the reference, kept for source compatibility (include/magma_zbatched.h:829-855).
  * Each factors the m x n block at (ai, aj) of every matrix: pivots are 1-based RELATIVE to row ai and written at
  * ipiv_array[b] + ai; a zero pivot at panel step i records gbstep + i + 1 in info_array[b] unless an earlier panel

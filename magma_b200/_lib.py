@@ -96,6 +96,11 @@ SIGNATURES = {
     "magma_b200_set_fused_max": (None, [i32]),
     "magma_b200_get_dgetrf_batched_crossover": (i32, [i32]),
     "magma_b200_rcp_selftest": (i64, [i64, vp]),
+    "magma_dgesv_rbt_batched": (i32, [i32, i32, vp, i32, vp, i32, vp, i32, vp]),
+    "magma_dgerbt_batched": (i32, [i32, i32, i32, vp, i32, vp, i32, vp, vp, vp, i32, vp]),
+    "magmablas_dprbt_batched": (None, [i32, vp, i32, vp, vp, i32, vp]),
+    "magmablas_dprbt_mv_batched": (None, [i32, i32, vp, vp, i32, i32, vp]),
+    "magmablas_dprbt_mtv_batched": (None, [i32, i32, vp, vp, i32, i32, vp]),
     "magma_dgetf2_fused_batched": (i32, [i32, i32, vp, i32, i32, i32, vp, vp, i32, vp]),
     "magma_dgetf2_batched": (i32, [i32, i32, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp]),
     "magma_dgetrf_recpanel_batched": (i32, [i32, i32, i32, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp]),

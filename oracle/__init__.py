@@ -228,3 +228,86 @@ def flops_getrf(m: float, n: float) -> float:
 def flops_getrs(n: float, nrhs: float) -> float:
     """FLOPS_DGETRS, testing/flops.h:90-91,284."""
     return nrhs * n * n + nrhs * n * (n - 1)
+
+
+# --------------------------------------------------------------------------------------------
+# Random butterfly transformation (SURVEY 8(f).2): numpy restatement of magmablas/zgerbt_kernels.cu:21-170 and of the
+# level order of magmablas/zgerbt_func_batched.cu:57-210 (z -> d). Every product and sum is rounded separately
+# (numpy never contracts into FMA), in the reference's operation order. u, v: arrays of 2n butterfly scalars.
+# --------------------------------------------------------------------------------------------
+def _rbt_block(A, Ai, Aj, Am, An, u, v):
+    """One butterfly level on the Am x An block at (Ai, Aj) of A[batch, col, row] (in place)."""
+    r1, c1 = (Am + 1) // 2, (An + 1) // 2
+    r2, c2 = Am - r1, An - c1
+    z = lambda cols, rows: np.zeros((A.shape[0], cols, rows))  # noqa: E731
+    a00 = A[:, Aj:Aj + c1, Ai:Ai + r1].copy()
+    a01, a10, a11 = z(c1, r1), z(c1, r1), z(c1, r1)
+    a01[:, :c2, :] = A[:, Aj + c1:Aj + c1 + c2, Ai:Ai + r1]
+    a10[:, :, :r2] = A[:, Aj:Aj + c1, Ai + r1:Ai + r1 + r2]
+    a11[:, :c2, :r2] = A[:, Aj + c1:Aj + c1 + c2, Ai + r1:Ai + r1 + r2]
+    u1, u2 = u[:r1], np.concatenate([u[r1:r1 + r2], np.zeros(r1 - r2)])
+    v1, v2 = v[:c1], np.concatenate([v[c1:c1 + c2], np.zeros(c1 - c2)])
+    b1, b2, b3, b4 = a00 + a01, a10 + a11, a00 - a01, a10 - a11
+    uv = lambda uu, vv: (uu[None, None, :] * vv[None, :, None])  # noqa: E731   (u * v) first, as the kernel does
+    A[:, Aj:Aj + c1, Ai:Ai + r1] = uv(u1, v1) * (b1 + b2)
+    A[:, Aj + c1:Aj + c1 + c2, Ai:Ai + r1] = (uv(u1, v2) * (b3 + b4))[:, :c2, :]
+    A[:, Aj:Aj + c1, Ai + r1:Ai + r1 + r2] = (uv(u2, v1) * (b1 - b2))[:, :, :r2]
+    A[:, Aj + c1:Aj + c1 + c2, Ai + r1:Ai + r1 + r2] = (uv(u2, v2) * (b3 - b4))[:, :c2, :r2]
+
+
+def prbt(A: np.ndarray, n: int, u: np.ndarray, v: np.ndarray):
+    """A <- U^T A V in place: inner level on the four quadrants (entries [n, 2n)), then the outer level ([0, n))."""
+    n1 = (n + 1) // 2
+    n2 = n - n1
+    ui, vi = u[n:], v[n:]
+    _rbt_block(A, 0, 0, n1, n1, ui[0:], vi[0:])
+    _rbt_block(A, 0, n1, n1, n2, ui[0:], vi[n1:])
+    _rbt_block(A, n1, 0, n2, n1, ui[n1:], vi[0:])
+    _rbt_block(A, n1, n1, n2, n2, ui[n1:], vi[n1:])
+    _rbt_block(A, 0, 0, n, n, u[0:], v[0:])
+
+
+def _rbt_vec(B, off, n, u, transpose):
+    if n < (2 if transpose else 1):
+        return
+    n1 = (n + 1) // 2
+    n2 = n - n1
+    top = B[:, :, off:off + n1].copy()
+    bot = np.zeros_like(top)
+    bot[:, :, :n2] = B[:, :, off + n1:off + n]
+    u0 = u[:n1]
+    u1 = np.concatenate([u[n1:n], np.zeros(n1 - n2)])
+    if transpose:
+        a1, a2 = top + bot, top - bot
+        B[:, :, off:off + n1] = u0 * a1
+        B[:, :, off + n1:off + n] = (u1 * a2)[:, :, :n2]
+    else:
+        a1, a2 = u0 * top, u1 * bot
+        B[:, :, off:off + n1] = a1 + a2
+        B[:, :, off + n1:off + n] = (a1 - a2)[:, :, :n2]
+
+
+def prbt_mtv(B: np.ndarray, n: int, u: np.ndarray):
+    """B <- U^T B in place (B[batch, nrhs, ld]): the two halves, then the outer level."""
+    n1 = (n + 1) // 2
+    _rbt_vec(B, 0, n1, u[n:], True)
+    _rbt_vec(B, n1, n - n1, u[n + n1:], True)
+    _rbt_vec(B, 0, n, u, True)
+
+
+def prbt_mv(B: np.ndarray, n: int, v: np.ndarray):
+    """B <- V B in place: the outer level, then the two halves."""
+    n1 = (n + 1) // 2
+    _rbt_vec(B, 0, n, v, False)
+    _rbt_vec(B, 0, n1, v[n:], False)
+    _rbt_vec(B, n1, n - n1, v[n + n1:], False)
+
+
+def gesv_rbt_batched(A: np.ndarray, B: np.ndarray, n: int, u: np.ndarray, v: np.ndarray):
+    """In place: butterflies, LU without pivoting, solves, X <- V Y (src/zgesv_rbt_batched.cpp:81-166). Returns info."""
+    prbt(A, n, u, v)
+    prbt_mtv(B, n, u)
+    info = getrf_nopiv_batched(A, n)
+    getrs_nopiv_batched(MagmaNoTrans, A, B, n)
+    prbt_mv(B, n, v)
+    return info

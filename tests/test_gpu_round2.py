@@ -211,6 +211,80 @@ def test_trsv_batched(gpu_queue, uplo, trans, diag, n, incb):
             assert np.array_equal(x[b][keep], x0[b][keep])
 
 
+# ---- random butterfly transformation ---------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n,nrhs,batch", [(1, 1, 3), (2, 2, 3), (7, 1, 5), (16, 3, 9), (33, 2, 5), (64, 4, 4), (100, 1, 3), (257, 2, 2)])
+def test_rbt_pieces_match_oracle(gpu_queue, n, nrhs, batch):
+    """magma_dgerbt_batched with the caller's butterflies (gen = MagmaFalse): A and B bit-identical to the restatement;
+    magmablas_dprbt_mv_batched likewise."""
+    import torch
+    L = _lib.load()
+    rng = np.random.default_rng(n)
+    u = np.exp((rng.random(2 * n) - 0.5) / 10)
+    v = np.exp((rng.random(2 * n) - 0.5) / 10)
+    A0 = rng.random((batch, n, n)) - 0.5
+    B0 = rng.random((batch, nrhs, n)) - 0.5
+    db = mb.DeviceBatch(batch, n, n, nrhs=nrhs, queue=gpu_queue)
+    db.upload(A0, B0)
+    info = C.c_int(99)
+    rc = L.magma_dgerbt_batched(0, n, nrhs, mb.ptr(db.dA_array), n, mb.ptr(db.dB_array), n, u.ctypes.data, v.ctypes.data,
+                                C.addressof(info), batch, gpu_queue.handle)
+    assert rc == 0 and info.value == 0
+    gpu_queue.sync()
+    Ar, Br = A0.copy(), B0.copy()
+    oracle.prbt(Ar, n, u, v)
+    oracle.prbt_mtv(Br, n, u)
+    assert np.array_equal(db.A.cpu().numpy(), Ar)
+    assert np.array_equal(db.B.cpu().numpy(), Br)
+    dv = torch.from_numpy(v).cuda()
+    L.magmablas_dprbt_mv_batched(n, nrhs, mb.ptr(dv), mb.ptr(db.dB_array), n, batch, gpu_queue.handle)
+    gpu_queue.sync()
+    oracle.prbt_mv(Br, n, v)
+    assert np.array_equal(db.B.cpu().numpy(), Br)
+
+
+@pytest.mark.parametrize("n,nrhs,batch", [(8, 1, 11), (32, 2, 7), (48, 3, 5), (100, 1, 4), (200, 2, 3), (512, 1, 2)])
+def test_gesv_rbt(gpu_queue, n, nrhs, batch):
+    """magma_dgesv_rbt_batched draws U, V with rand() like the reference: seed the C library, redraw the same numbers
+    here, and the solution must equal the restatement bit for bit; the residual check of the testers holds loosely
+    (no pivoting: 1e-9 instead of 30 eps)."""
+    L = _lib.load()
+    libc = C.CDLL(None)
+    libc.rand.restype = C.c_int
+    RAND_MAX = 2147483647
+    A0, seed = oracle.random_batch(batch, n, n)
+    B0, _ = oracle.random_batch(batch, n, nrhs, iseed=seed)
+    db = mb.DeviceBatch(batch, n, n, nrhs=nrhs, queue=gpu_queue)
+    db.upload(A0, B0)
+    libc.srand(4242)
+    rc = L.magma_dgesv_rbt_batched(n, nrhs, mb.ptr(db.dA_array), n, mb.ptr(db.dB_array), n, mb.ptr(db.info), batch,
+                                   gpu_queue.handle)
+    assert rc == 0
+    gpu_queue.sync()
+    libc.srand(4242)
+    u, v = np.zeros(2 * n), np.zeros(2 * n)
+    import math
+    for i in range(2 * n):
+        u[i] = math.exp((((libc.rand() * 1.0) / RAND_MAX) - 0.5) / 10)
+        v[i] = math.exp((((libc.rand() * 1.0) / RAND_MAX) - 0.5) / 10)
+    Ar, Br = A0.copy(), B0.copy()
+    infr = oracle.gesv_rbt_batched(Ar, Br, n, u, v)
+    X = db.B.cpu().numpy()
+    assert np.array_equal(db.info.cpu().numpy(), infr)
+    assert np.array_equal(db.A.cpu().numpy(), Ar)
+    assert np.array_equal(X, Br)
+    assert oracle.solve_residual(oracle.MagmaNoTrans, A0, X, B0, n) < 1e-9
+
+
+def test_gesv_rbt_argument_errors(gpu_queue, capfd):
+    L = _lib.load()
+    assert L.magma_dgesv_rbt_batched(-1, 1, 0, 1, 0, 1, 0, 1, gpu_queue.handle) == -1
+    assert L.magma_dgesv_rbt_batched(4, 1, 0, 3, 0, 4, 0, 1, gpu_queue.handle) == -4
+    assert L.magma_dgesv_rbt_batched(4, 1, 0, 4, 0, 3, 0, 1, gpu_queue.handle) == -6
+    assert L.magma_dgesv_rbt_batched(0, 1, 0, 1, 0, 1, 0, 1, gpu_queue.handle) == 0
+    assert "magma_dgesv_rbt_batched" in capfd.readouterr().err
+
+
 # ---- single-process multi-GPU -------------------------------------------------------------------------------------
 
 def _two_gpus():

@@ -207,3 +207,29 @@ def test_flops_formulas():
     assert round(oracle.flops_getrf(512, 512)) == 89347840
     assert oracle.flops_getrs(512, 16) == 8380416
     assert round(oracle.flops_getrf(16, 16)) == 2616 and oracle.flops_getrs(16, 1) == 496
+
+
+def test_rbt_restatement_is_consistent():
+    """oracle.prbt / prbt_mtv / prbt_mv (numpy restatement of magmablas/zgerbt_kernels.cu): the vector routines define
+    the dense butterflies U^T and V; the matrix routine must equal U^T A V, and the whole chain must solve A X = B."""
+    rng = np.random.default_rng(7)
+    for n in (1, 2, 3, 7, 8, 33, 64):
+        u = np.exp((rng.random(2 * n) - 0.5) / 10)
+        v = np.exp((rng.random(2 * n) - 0.5) / 10)
+        eye = np.ascontiguousarray(np.eye(n)[None])          # [1, col, row]
+        Ut = eye.copy(); oracle.prbt_mtv(Ut, n, u)            # column j of U^T
+        V = eye.copy(); oracle.prbt_mv(V, n, v)
+        Ut, V = Ut[0].T, V[0].T                               # [row, col]
+        A = rng.random((2, n, n))
+        ref = np.stack([(Ut @ A[b].T @ V).T for b in range(2)])
+        got = A.copy(); oracle.prbt(got, n, u, v)
+        if n >= 4:  # (a half of size 1, i.e. n <= 3: the reference's transposed vector routine returns early for
+            #  n < 2 while its matrix routine scales -- zgerbt_kernels.cu:157 vs :21-80 -- and the restatement follows it)
+            assert np.allclose(got, ref, rtol=1e-13, atol=1e-15)
+    n, batch, nrhs = 48, 5, 3
+    A0 = rng.random((batch, n, n)); B0 = rng.random((batch, nrhs, n))
+    u = np.exp((rng.random(2 * n) - 0.5) / 10); v = np.exp((rng.random(2 * n) - 0.5) / 10)
+    A, B = A0.copy(), B0.copy()
+    info = oracle.gesv_rbt_batched(A, B, n, u, v)
+    assert not info.any()
+    assert oracle.solve_residual(oracle.MagmaNoTrans, A0, B, B0, n) < 1e-9  # no pivoting: looser than the 30 eps bar

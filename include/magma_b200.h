@@ -312,12 +312,28 @@ void magma_dlaswp_rowparallel_batched(magma_int_t n, double **input_array, magma
 void magmablas_dtrsv_batched(magma_uplo_t uplo, magma_trans_t transA, magma_diag_t diag, magma_int_t n, double **dA_array,
                              magma_int_t ldda, double **dB_array, magma_int_t incb, magma_int_t batchCount,
                              magma_queue_t queue);
-/* B_b <- alpha * op(A_b)^-1 B_b, side = Left only on this path.   magmablas/ztrsm_batched_core.cpp:299-350 */
+/* side = Left: B_b <- alpha op(A_b)^-1 B_b; side = Right: B_b <- alpha B_b op(A_b)^-1.   magmablas/ztrsm_batched_core.cpp:299-350 */
 void magmablas_dtrsm_batched(magma_side_t side, magma_uplo_t uplo, magma_trans_t transA, magma_diag_t diag,
                              magma_int_t m, magma_int_t n, double alpha, double **dA_array, magma_int_t ldda,
                              double **dB_array, magma_int_t lddb, magma_int_t batchCount, magma_queue_t queue);
-/* C_b(Ci.., Cj..) <- alpha A_b(Ai.., Aj..) B_b(Bi.., Bj..) + beta C_b, NoTrans/NoTrans only.
- * magmablas/zgemm_batched.cpp:49-100 */
+/* C_b <- alpha op(A_b) op(B_b) + beta C_b on the FP64 tensor pipe, any transposes.  magmablas/zgemm_batched.cpp:269-286 */
+void magma_dgemm_batched(magma_trans_t transA, magma_trans_t transB, magma_int_t m, magma_int_t n, magma_int_t k,
+                         double alpha, double const *const *dA_array, magma_int_t ldda, double const *const *dB_array,
+                         magma_int_t lddb, double beta, double **dC_array, magma_int_t lddc, magma_int_t batchCount,
+                         magma_queue_t queue);
+/* Strided device front ends (new surface): matrix b at dA + b*strideA (elements), pivots at
+ * dipiv + b*stride_piv, right-hand sides at dB + b*strideB. Same results and return codes as the pointer-array forms. */
+magma_int_t magma_dgetrf_batched_strided(magma_int_t m, magma_int_t n, double *dA, magma_int_t ldda, magma_int_t strideA,
+                                         magma_int_t *dipiv, magma_int_t stride_piv, magma_int_t *info_array,
+                                         magma_int_t batchCount, magma_queue_t queue);
+magma_int_t magma_dgetrs_batched_strided(magma_trans_t trans, magma_int_t n, magma_int_t nrhs, double *dA, magma_int_t ldda,
+                                         magma_int_t strideA, magma_int_t *dipiv, magma_int_t stride_piv, double *dB,
+                                         magma_int_t lddb, magma_int_t strideB, magma_int_t batchCount, magma_queue_t queue);
+magma_int_t magma_dgesv_batched_strided(magma_int_t n, magma_int_t nrhs, double *dA, magma_int_t ldda, magma_int_t strideA,
+                                        magma_int_t *dipiv, magma_int_t stride_piv, double *dB, magma_int_t lddb,
+                                        magma_int_t strideB, magma_int_t *dinfo_array, magma_int_t batchCount,
+                                        magma_queue_t queue);
+/* C_b(Ci.., Cj..) <- alpha op(A_b)(Ai.., Aj..) op(B_b)(Bi.., Bj..) + beta C_b.   magmablas/zgemm_batched.cpp:49-100 */
 void magma_dgemm_batched_core(magma_trans_t transA, magma_trans_t transB, magma_int_t m, magma_int_t n, magma_int_t k,
                               double alpha, double const *const *dA_array, magma_int_t Ai, magma_int_t Aj, magma_int_t ldda,
                               double const *const *dB_array, magma_int_t Bi, magma_int_t Bj, magma_int_t lddb,

@@ -96,6 +96,10 @@ SIGNATURES = {
     "magma_b200_set_fused_max": (None, [i32]),
     "magma_b200_get_dgetrf_batched_crossover": (i32, [i32]),
     "magma_b200_rcp_selftest": (i64, [i64, vp]),
+    "magma_dgemm_batched": (None, [i32, i32, i32, i32, i32, dbl, vp, i32, vp, i32, dbl, vp, i32, i32, vp]),
+    "magma_dgetrf_batched_strided": (i32, [i32, i32, vp, i32, i32, vp, i32, vp, i32, vp]),
+    "magma_dgetrs_batched_strided": (i32, [i32, i32, i32, vp, i32, i32, vp, i32, vp, i32, i32, i32, vp]),
+    "magma_dgesv_batched_strided": (i32, [i32, i32, vp, i32, i32, vp, i32, vp, i32, i32, vp, i32, vp]),
     "magma_dgesv_rbt_batched": (i32, [i32, i32, vp, i32, vp, i32, vp, i32, vp]),
     "magma_dgerbt_batched": (i32, [i32, i32, i32, vp, i32, vp, i32, vp, vp, vp, i32, vp]),
     "magmablas_dprbt_batched": (None, [i32, vp, i32, vp, vp, i32, vp]),

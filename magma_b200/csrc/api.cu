@@ -520,13 +520,12 @@ void magmablas_dtrsm_batched(magma_side_t side, magma_uplo_t uplo, magma_trans_t
     else if (n < 0) info = -6;
     else if (ldda < imax(1, side == MagmaLeft ? m : n)) info = -9;
     else if (lddb < imax(1, m)) info = -11;
-    if (info == 0 && side == MagmaRight) {
-        // the LU path only ever solves from the left; say so instead of computing something else
-        magma_xerbla(__func__, -MAGMA_ERR_NOT_IMPLEMENTED);
-        return;
-    }
     if (info != 0) {
         magma_xerbla(__func__, -info);
+        return;
+    }
+    if (side == MagmaRight) {
+        trsm_right_launch(uplo, transA, diag, m, n, alpha, dA_array, ldda, dB_array, lddb, batchCount, MB200_Q(queue)->stream);
         return;
     }
     trsm_left_launch(uplo, transA, diag, m, n, alpha, dA_array, ldda, dB_array, lddb, batchCount, MB200_Q(queue)->stream);
@@ -538,12 +537,27 @@ void magma_dgemm_batched_core(magma_trans_t transA, magma_trans_t transB, magma_
                               magma_int_t Bj, magma_int_t lddb, double beta, double **dC_array, magma_int_t Ci,
                               magma_int_t Cj, magma_int_t lddc, magma_int_t batchCount, magma_queue_t queue)
 {
-    if (transA != MagmaNoTrans || transB != MagmaNoTrans) {
-        magma_xerbla(__func__, -MAGMA_ERR_NOT_IMPLEMENTED);
+    magma_int_t info = 0;
+    if (transA != MagmaNoTrans && transA != MagmaTrans && transA != MagmaConjTrans) info = -1;
+    else if (transB != MagmaNoTrans && transB != MagmaTrans && transB != MagmaConjTrans) info = -2;
+    else if (m < 0) info = -3;
+    else if (n < 0) info = -4;
+    else if (k < 0) info = -5;
+    else if (ldda < imax(1, transA == MagmaNoTrans ? m : k)) info = -8;
+    else if (lddb < imax(1, transB == MagmaNoTrans ? k : n)) info = -10;
+    else if (lddc < imax(1, m)) info = -13;
+    if (info != 0) {
+        magma_xerbla(__func__, -info);
         return;
     }
-    gemm_nn_launch(m, n, k, alpha, dA_array, Ai, Aj, ldda, dB_array, Bi, Bj, lddb, beta, dC_array, Ci, Cj, lddc,
-                   batchCount, MB200_Q(queue)->stream);
+    if (g_tier == 4)  // DFMA kernels only (A/B runs): the SIMT tile, NoTrans x NoTrans
+        if (transA == MagmaNoTrans && transB == MagmaNoTrans) {
+            gemm_nn_launch(m, n, k, alpha, dA_array, Ai, Aj, ldda, dB_array, Bi, Bj, lddb, beta, dC_array, Ci, Cj, lddc,
+                           batchCount, MB200_Q(queue)->stream);
+            return;
+        }
+    gemm_dmma_launch(transA, transB, m, n, k, alpha, dA_array, Ai, Aj, ldda, dB_array, Bi, Bj, lddb, beta, dC_array, Ci, Cj,
+                     lddc, batchCount, MB200_Q(queue)->stream);
 }
 
 void magma_dset_pointer(double **output_array, double *input, magma_int_t lda, magma_int_t row, magma_int_t column,

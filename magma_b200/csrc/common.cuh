@@ -179,6 +179,13 @@ void gemm_nn_launch(int m, int n, int k, double alpha, double const *const *dA, 
                     int ldda, double const *const *dB, int Bi, int Bj, int lddb, double beta,
                     double **dC, int Ci, int Cj, int lddc, long batch, cudaStream_t s);
 
+// blas3.cu: C <- alpha op(A) op(B) + beta C on the FP64 tensor pipe; X op(A) = alpha B
+void gemm_dmma_launch(int transA, int transB, int m, int n, int k, double alpha, double const *const *dA, int Ai, int Aj,
+                      int ldda, double const *const *dB, int Bi, int Bj, int lddb, double beta, double **dC, int Ci, int Cj,
+                      int lddc, long batch, cudaStream_t s);
+void trsm_right_launch(int uplo, int trans, int diag, int m, int n, double alpha, double **dA, int ldda, double **dB,
+                       int lddb, long batch, cudaStream_t s);
+
 // aux.cu
 void set_pointer_launch(void **out, char *base, long elem, long lda, long row, long col,
                         long batch_offset, long batch, cudaStream_t s);

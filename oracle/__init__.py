@@ -72,6 +72,7 @@ def lib():
         L.oracle_solve_residual_batched.argtypes = [_i, _i, _i, _pd, _i, _l, _pd, _i, _l, _pd, _i,
                                                     _l, _l]
         L.oracle_solve_residual_batched.restype = _d
+        L.oracle_dgemm_lu_update.argtypes = [_i, _i, _i, _pd, _i, _pd, _i, _pd, _i]
         L.oracle_num_threads.restype = _i
         _lib = L
     return _lib
@@ -311,3 +312,11 @@ def gesv_rbt_batched(A: np.ndarray, B: np.ndarray, n: int, u: np.ndarray, v: np.
     getrs_nopiv_batched(MagmaNoTrans, A, B, n)
     prbt_mv(B, n, v)
     return info
+
+
+def gemm_lu_update(A: np.ndarray, B: np.ndarray, Cm: np.ndarray):
+    """C <- C - A B per element as the chain fma(-a(i,k), b(k,j), c), k increasing (lu_oracle.c). Arrays are single
+    matrices in the stored layout [col, row] (column-major), updated in place: A[k, m], B[n, k], C[n, m]."""
+    k, m = A.shape
+    n = B.shape[0]
+    lib().oracle_dgemm_lu_update(m, n, k, A.reshape(-1), m, B.reshape(-1), B.shape[1], Cm.reshape(-1), Cm.shape[1])

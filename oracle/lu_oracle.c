@@ -386,3 +386,18 @@ int oracle_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------
+ * The LU trailing update as a stand-alone product (magma_dgemm_batched with alpha = -1, beta = 1, NoTrans/NoTrans:
+ * src/zgetrf_batched.cpp:195-200 calls magma_zgemm_batched_core this way): per element the canonical chain
+ *     c(i,j) <- fma(-a(i,k), b(k,j), c(i,j)),  k = 0 .. K-1 in increasing order.
+ * ------------------------------------------------------------------------------------------ */
+void oracle_dgemm_lu_update(int m, int n, int k, const double *A, int lda, const double *B, int ldb, double *C, int ldc)
+{
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < m; ++i) {
+            double c = C[i + (size_t)j * ldc];
+            for (int kk = 0; kk < k; ++kk) c = fma(-A[i + (size_t)kk * lda], B[kk + (size_t)j * ldb], c);
+            C[i + (size_t)j * ldc] = c;
+        }
+}

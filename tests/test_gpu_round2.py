@@ -211,6 +211,117 @@ def test_trsv_batched(gpu_queue, uplo, trans, diag, n, incb):
             assert np.array_equal(x[b][keep], x0[b][keep])
 
 
+# ---- standalone BLAS-3 and strided front ends -----------------------------------------------------------------------
+
+def _ptrs(t, stride_elems, batch, esize=8):
+    import torch
+    return torch.tensor([t.data_ptr() + esize * stride_elems * b for b in range(batch)], dtype=torch.int64, device="cuda")
+
+
+@pytest.mark.parametrize("ta", [mb.MagmaNoTrans, mb.MagmaTrans])
+@pytest.mark.parametrize("tb", [mb.MagmaNoTrans, mb.MagmaTrans])
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (7, 5, 3), (64, 64, 16), (65, 63, 17), (100, 130, 45), (200, 96, 128)])
+def test_dgemm_batched_all_transposes(gpu_queue, ta, tb, m, n, k):
+    import torch
+    L = _lib.load()
+    batch = 3
+    rng = np.random.default_rng(m * 1000 + n * 10 + k)
+    ar, ac = (m, k) if ta == mb.MagmaNoTrans else (k, m)
+    br, bc = (k, n) if tb == mb.MagmaNoTrans else (n, k)
+    A = rng.random((batch, ac, ar + 2)) - 0.5      # stored [col, row], lda = ar + 2
+    B = rng.random((batch, bc, br + 1)) - 0.5
+    Cm = rng.random((batch, n, m + 3)) - 0.5
+    dA, dB, dC = (torch.from_numpy(x).cuda() for x in (A, B, Cm))
+    pa, pb, pc = _ptrs(dA, A[0].size, batch), _ptrs(dB, B[0].size, batch), _ptrs(dC, Cm[0].size, batch)  # kept alive
+    for alpha, beta in ((1.5, -0.5), (2.0, 0.0), (-1.0, 1.0)):
+        dC.copy_(torch.from_numpy(Cm))
+        L.magma_dgemm_batched(ta, tb, m, n, k, alpha, mb.ptr(pa), ar + 2, mb.ptr(pb), br + 1, beta, mb.ptr(pc), m + 3,
+                              batch, gpu_queue.handle)
+        gpu_queue.sync()
+        got = dC.cpu().numpy()
+        for b in range(batch):
+            Am = A[b].T[:ar, :ac]
+            Bm = B[b].T[:br, :bc]
+            opA = Am if ta == mb.MagmaNoTrans else Am.T
+            opB = Bm if tb == mb.MagmaNoTrans else Bm.T
+            ref = alpha * (opA @ opB) + beta * Cm[b].T[:m, :n]
+            assert np.allclose(got[b].T[:m, :n], ref, rtol=1e-12, atol=1e-12)
+            assert np.array_equal(got[b].T[m:, :], Cm[b].T[m:, :]), "wrote into the ldc padding"
+
+
+@pytest.mark.parametrize("m,n,k", [(64, 64, 32), (130, 70, 64), (33, 200, 100)])
+def test_dgemm_batched_lu_update_is_canonical(gpu_queue, m, n, k):
+    """alpha = -1, beta = 1 (the LU trailing update): bit-identical to the fma chain with k increasing."""
+    import torch
+    L = _lib.load()
+    batch = 2
+    rng = np.random.default_rng(k)
+    A = rng.random((batch, k, m)); B = rng.random((batch, n, k)); Cm = rng.random((batch, n, m))
+    dA, dB, dC = (torch.from_numpy(x).cuda() for x in (A, B, Cm))
+    pa, pb, pc = _ptrs(dA, A[0].size, batch), _ptrs(dB, B[0].size, batch), _ptrs(dC, Cm[0].size, batch)  # kept alive
+    L.magma_dgemm_batched(mb.MagmaNoTrans, mb.MagmaNoTrans, m, n, k, -1.0, mb.ptr(pa), m, mb.ptr(pb), k, 1.0, mb.ptr(pc), m,
+                          batch, gpu_queue.handle)
+    gpu_queue.sync()
+    got = dC.cpu().numpy()
+    for b in range(batch):
+        ref = Cm[b].copy()
+        oracle.gemm_lu_update(np.ascontiguousarray(A[b]), np.ascontiguousarray(B[b]), ref)
+        assert np.array_equal(got[b], ref)
+
+
+@pytest.mark.parametrize("uplo", [mb.MagmaLower, mb.MagmaUpper])
+@pytest.mark.parametrize("trans", [mb.MagmaNoTrans, mb.MagmaTrans])
+@pytest.mark.parametrize("diag", [mb.MagmaUnit, mb.MagmaNonUnit])
+@pytest.mark.parametrize("m,n", [(1, 1), (5, 31), (130, 33), (40, 100)])
+def test_dtrsm_batched_right(gpu_queue, uplo, trans, diag, m, n):
+    import torch
+    batch = 3
+    rng = np.random.default_rng(m + 7 * n)
+    T = rng.random((batch, n, n)) + n * np.eye(n)
+    B = rng.random((batch, n, m + 1)) - 0.5       # m x n stored [col, row], ldb = m + 1
+    dT, dB = torch.from_numpy(T).cuda(), torch.from_numpy(B).cuda()
+    pt, pb = _ptrs(dT, n * n, batch), _ptrs(dB, B[0].size, batch)  # kept alive until the sync
+    mb.magmablas_dtrsm_batched(mb.MagmaRight, uplo, trans, diag, m, n, 1.5, pt, n, pb, m + 1, batch, gpu_queue)
+    gpu_queue.sync()
+    X = dB.cpu().numpy()
+    for b in range(batch):
+        Tm = T[b].T
+        Tm = np.tril(Tm) if uplo == mb.MagmaLower else np.triu(Tm)
+        if diag == mb.MagmaUnit:
+            Tm = Tm - np.diag(np.diag(Tm)) + np.eye(n)
+        op = Tm if trans == mb.MagmaNoTrans else Tm.T
+        ref = 1.5 * B[b].T[:m, :] @ np.linalg.inv(op)
+        assert np.allclose(X[b].T[:m, :], ref, rtol=1e-10, atol=1e-12)
+        assert np.array_equal(X[b].T[m:, :], B[b].T[m:, :])
+
+
+@pytest.mark.parametrize("n,nrhs,batch", [(16, 1, 300), (40, 2, 30), (130, 3, 5)])
+def test_strided_front_ends(gpu_queue, n, nrhs, batch):
+    """dA + b*stride forms: same results as the pointer-array entry points (and hence as the oracle)."""
+    import torch
+    L = _lib.load()
+    A0, seed = oracle.random_batch(batch, n, n)
+    B0, _ = oracle.random_batch(batch, n, nrhs, iseed=seed)
+    Ar, Br = A0.copy(), B0.copy()
+    ipr, infr = oracle.gesv_batched(Ar, Br, n)
+    dA, dB = torch.from_numpy(A0).cuda(), torch.from_numpy(B0).cuda()
+    ip = torch.zeros((batch, n), dtype=torch.int32, device="cuda")
+    info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    assert L.magma_dgesv_batched_strided(n, nrhs, mb.ptr(dA), n, n * n, mb.ptr(ip), n, mb.ptr(dB), n, n * nrhs, mb.ptr(info),
+                                         batch, gpu_queue.handle) == 0
+    gpu_queue.sync()
+    assert np.array_equal(ip.cpu().numpy(), ipr) and np.array_equal(dA.cpu().numpy(), Ar)
+    assert np.array_equal(dB.cpu().numpy(), Br)
+    # getrf + getrs, strided
+    dA.copy_(torch.from_numpy(A0)); dB.copy_(torch.from_numpy(B0))
+    assert L.magma_dgetrf_batched_strided(n, n, mb.ptr(dA), n, n * n, mb.ptr(ip), n, mb.ptr(info), batch, gpu_queue.handle) == 0
+    assert L.magma_dgetrs_batched_strided(mb.MagmaNoTrans, n, nrhs, mb.ptr(dA), n, n * n, mb.ptr(ip), n, mb.ptr(dB), n,
+                                          n * nrhs, batch, gpu_queue.handle) == 0
+    gpu_queue.sync()
+    assert np.array_equal(dA.cpu().numpy(), Ar) and np.array_equal(ip.cpu().numpy(), ipr)
+    assert np.array_equal(dB.cpu().numpy(), Br)
+
+
 # ---- random butterfly transformation ---------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("n,nrhs,batch", [(1, 1, 3), (2, 2, 3), (7, 1, 5), (16, 3, 9), (33, 2, 5), (64, 4, 4), (100, 1, 3), (257, 2, 2)])

@@ -6,7 +6,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libmagma_b200.so")
+LIB_PATH = os.environ.get("MB200_LIB") or os.path.join(HERE, "lib", "libmagma_b200.so")  # MB200_LIB: A/B runs of two builds
 HEADER = os.path.join(os.path.dirname(HERE), "include", "magma_b200.h")
 
 _lib = None

@@ -1108,16 +1108,18 @@ template <int NW>
 struct LeftSmem {
     static constexpr int RING = (NW == 4) ? 3 : 4;  // chunks in the ring
     static constexpr int LDR = NW * 32 + 4;         // As[kk*LDR + row]: A fragments (k = 4s+q, row 8t+g) hit 32 distinct banks
-    double Us[32 * LL_LDU];                 // block row K of the slab as the owners left it
+    unsigned short rmap[NW][NW * 32];       // row i of the current order -> row in the order of panel K
+    unsigned short src[NW * 32];            // row i of the current order -> original row (slab load)
+    unsigned short sinv_s[NW][NW * 32];     // the recorded step permutations while the maps are built
+    unsigned long long full[RING], empty[RING], lsbar, stbar;
+    // ---- from here on one contiguous region: at kernel start it receives the whole slab (32 columns, stride LDR) by
+    // TMA while the maps are being built; afterwards its parts take their own roles
+    alignas(16) double Us[32 * LL_LDU];     // block row K of the slab as the owners left it
     double Un[32 * LL_LDU];                 // -U(K, J): written by the solve of step K (between the step's two
                                             // barriers), read by its ring pass; every warp is past that pass when
                                             // the next solve starts, so one buffer is enough
-    alignas(16) double Ls[32 * 33];         // L_KK, column-major [k*32 + i]: read by the solve, refilled (TMA / cp.async) during the ring pass
-    unsigned short rmap[NW][NW * 32];       // row i of the current order -> row in the order of panel K
-    unsigned short src[NW * 32];            // row i of the current order -> original row (slab load)
-    unsigned long long full[RING], empty[RING], lsbar, stbar;
-    alignas(16) double ring[RING * 8 * LDR];  // L chunks, CTA-wide, rows in the order of their own panel; the staged
-                                            // step permutations (NW x NW*32 shorts) live here during set-up
+    alignas(16) double Ls[32 * 33];         // L_KK [k*32 + slot(i)]: read by the solve, refilled (cp.async) during the ring pass
+    alignas(16) double ring[RING * 8 * LDR];  // L chunks, CTA-wide, rows in the order of their own panel
 };
 
 template <int NW>
@@ -1154,8 +1156,35 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
     const int g = lane >> 2, q = lane & 3;
     double *__restrict__ A = dA[b];
 
+    constexpr int LDR = LeftSmem<NW>::LDR;
+    static_assert(sizeof(double) * 32 * LDR <= sizeof(double) * (2 * 32 * LL_LDU + 32 * 33 + RING * 8 * LDR), "slab staging region");
+    const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const bool bulk_ok = vec_ok && ((m & 1) == 0) && (use_bulk != 0);  // 16-byte aligned columns of a multiple of 16 bytes
+    if (tid == 0) {
+        for (int i = 0; i < RING; ++i) {
+            ll_mbar_init(&S.full[i], T);
+            ll_mbar_init(&S.empty[i], T);
+        }
+        ll_mbar_init(&S.lsbar, T);
+        ll_mbar_init(&S.stbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // ---- the slab: one TMA bulk copy per column into the staging region, in flight while the maps are built ------
+    double *const stage = S.Us;
+    if (bulk_ok && tid < 32) {
+        if (tid == 0) {
+            int ncopy = 0;
+            for (int cc = 0; cc < 32; ++cc) ncopy += (cc >= cb && cc < nc) ? 1 : 0;
+            asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(&S.stbar)),
+                         "r"((unsigned)ncopy * (unsigned)m * 8u)
+                         : "memory");
+        }
+        if (tid >= cb && tid < nc) ll_bulk_load(stage + tid * LDR, A + (size_t)(c0 + tid) * ld, (unsigned)m * 8u, &S.stbar);
+    }
     // ---- row maps ----------------------------------------------------------------------------------------
-    unsigned short(*sinv_s)[T] = reinterpret_cast<unsigned short(*)[T]>(S.ring);
+    unsigned short(*sinv_s)[T] = S.sinv_s;
     {
         const unsigned short *sg = sinv_g + (size_t)slot * sinv_blocks * sinv_rows;
         for (int K = kfirst; K < nk; ++K) sinv_s[K][tid] = (tid < m) ? sg[(size_t)K * sinv_rows + tid] : (unsigned short)tid;
@@ -1169,7 +1198,7 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
         }
         S.src[tid] = (unsigned short)r;
     }
-    __syncthreads();  // maps complete; the ring may be overwritten
+    __syncthreads();  // maps complete
 
     // ---- L chunk pipeline: chunk 4K+ch = columns 32K+8ch .. +8 of L, every row below block row K, copied in the
     // row order of panel K itself: contiguous 16-byte cp.asyncs (the first version gathered each warp's rows through
@@ -1177,9 +1206,6 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
     // bytes, 63% of all LSU wavefronts of the kernel). The permutation is applied when the A fragments are READ from
     // shared memory (rmap, word granular). Slots are handed over with mbarriers: full[] counts the threads'
     // cp.async completions, empty[] the threads that are done reading.
-    constexpr int LDR = LeftSmem<NW>::LDR;
-    const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-    const bool bulk_ok = vec_ok && ((m & 1) == 0) && (use_bulk != 0);  // 16-byte aligned columns of a multiple of 16 bytes
     auto issue = [&](int nrel) {  // nrel: chunk number counted from the first step
         const int K = kfirst + (nrel >> 2), ch = nrel & 3;
         const int slot_r = nrel % RING;
@@ -1236,7 +1262,7 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
     auto stage_lkk = [&](int K) {  // L_KK -> Ls, zero outside the panel width
         const int kbK = (kend - 32 * K) < 32 ? (kend - 32 * K) : 32;
         const double *LKK = A + (size_t)(32 * K) + (size_t)(32 * K) * ld;
-        if (bulk_ok && (use_bulk & 2) && kbK == 32) {  // TMA: 32 columns of 256 bytes
+        if (false && bulk_ok && (use_bulk & 2) && kbK == 32) {  // TMA variant (plain column layout): measured slower, retired
             if (tid < 32) {
                 if (tid == 0) ll_mbar_expect_tx(&S.lsbar, 32u * 256u);
                 ll_bulk_load(&S.Ls[tid * 32], LKK + (size_t)tid * ld, 256u, &S.lsbar);
@@ -1245,48 +1271,39 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             for (int idx = tid; idx < 1024; idx += T) {
                 const int i = idx & 31, k = idx >> 5;
                 const bool ok = (i < kbK && k < kbK);
-                cp_async8(&S.Ls[k * 32 + i], ok ? LKK + i + (size_t)k * ld : A, ok);
+                // NW = 4: per column k the 32 multipliers sit in the order the solving lanes read them (a lane's rows
+                // rg + 4 i8 at rg*8 + i8: LDS.128). Wider CTAs keep the plain order (the same change cost them 1.5%).
+                const int slot_i = (NW == 4) ? ((i & 3) * 8 + (i >> 2)) : i;
+                cp_async8(&S.Ls[k * 32 + slot_i], ok ? LKK + i + (size_t)k * ld : A, ok);
             }
         }
         ll_mbar_arrive_cp_async(&S.lsbar);
     };
-    if (tid == 0) {
-        for (int i = 0; i < RING; ++i) {
-            ll_mbar_init(&S.full[i], T);
-            ll_mbar_init(&S.empty[i], T);
-        }
-        ll_mbar_init(&S.lsbar, T);
-        ll_mbar_init(&S.stbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    stage_lkk(kfirst);
 
     // ---- the slab, rows in current order ---------------------------------------------------------------------
     // Copied with contiguous 16-byte cp.asyncs (original row order) into the ring, which the L chunks do not need
     // yet, and picked up through src[] from shared memory: the direct gather cost 26 tag requests per 8-byte warp load
     // and a fifth of the kernel's time on the middle slabs.
-    constexpr int SCOLS = (RING * 8 >= 32) ? 32 : 16;  // slab columns the ring can hold at once
+    constexpr int SCOLS = (RING * 8 >= 32) ? 32 : 16;  // slab columns the ring can hold at once (LDGSTS path)
     double acc[4][4][2];
+    if (bulk_ok) {
+        ll_mbar_wait(&S.stbar, 0u);  // all 32 columns have landed
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int row = 8 * (w + NW * a) + g;
+            const bool rok = row < m;
+            const double *sp = stage + (rok ? (int)S.src[row] : 0) + (2 * q) * LDR;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                acc[a][c][0] = rok ? sp[(8 * c) * LDR] : 0.0;
+                acc[a][c][1] = rok ? sp[(8 * c + 1) * LDR] : 0.0;
+            }
+        }
+        __syncthreads();  // the staging region is free: its parts take their own roles
+    } else {
 #pragma unroll
     for (int p0 = 0; p0 < 32; p0 += SCOLS) {
-        if (bulk_ok) {
-            // TMA: one bulk copy per slab column (columns outside [cb, nc) are not staged: their accumulators are
-            // never stored)
-            if (tid < SCOLS) {
-                if (tid == 0) {
-                    int ncopy = 0;
-                    for (int cc = 0; cc < SCOLS; ++cc) ncopy += (p0 + cc >= cb && p0 + cc < nc) ? 1 : 0;
-                    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
-                                     (unsigned)__cvta_generic_to_shared(&S.stbar)),
-                                 "r"((unsigned)ncopy * (unsigned)m * 8u)
-                                 : "memory");
-                }
-                const int col = p0 + tid;
-                if (col >= cb && col < nc) ll_bulk_load(S.ring + tid * LDR, A + (size_t)(c0 + col) * ld, (unsigned)m * 8u, &S.stbar);
-            }
-            ll_mbar_wait(&S.stbar, (unsigned)((p0 / SCOLS) & 1));
-        } else if (vec_ok) {
+        if (vec_ok) {
             const int npairs = (m + 1) >> 1;
             const unsigned magic = 0xFFFFFFFFu / (unsigned)npairs + 1u;
             for (int u = tid; u < SCOLS * npairs; u += T) {
@@ -1308,10 +1325,8 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
                 cp_async8(S.ring + cc * LDR + r, ok ? A + r + (size_t)(c0 + col) * ld : A, ok);
             }
         }
-        if (!bulk_ok) {
-            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-            __syncthreads();
-        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int row = 8 * (w + NW * a) + g;
@@ -1327,6 +1342,8 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
         }
         __syncthreads();  // the ring is free again; every row of these columns is in registers
     }
+    }
+    stage_lkk(kfirst);
 #pragma unroll 1
     for (int pch = 0; pch < ahead; ++pch) issue(pch);
 
@@ -1387,19 +1404,31 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             // four warps (at most 128 rows): column 8w + lane%8, rows lane/8 + 4i (i < 8) per lane
             const int cl = lane & 7, rg = lane >> 3;
             const int cc = 8 * w + cl;
-            const double *Lk = S.Ls;
+            const unsigned lk = (unsigned)__cvta_generic_to_shared(S.Ls) + (unsigned)(rg * 8) * 8u;
             double x[8];
 #pragma unroll
             for (int i8 = 0; i8 < 8; ++i8) x[i8] = S.Us[(rg + 4 * i8) * LL_LDU + cc];
+            // the multipliers of step k + 1 are fetched (LDS.128 into their own registers) before the DFMAs of step k:
+            // written as `l = Ls[..]` per use, ptxas recycled ONE register pair for every load, so each DFMA waited out
+            // a full shared-memory latency (ncu: 8 exposed LDS per step). n = 128: 10.47 -> 9.87 ms on the same box.
+            double lb[2][8];
+            auto load_l = [&](double (&dst)[8], int k) {  // only the pairs that still have rows below k (static)
+#pragma unroll
+                for (int p2 = 0; p2 < 4; ++p2)
+                    if (4 * (2 * p2 + 1) + 3 > k)
+                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(dst[2 * p2]), "=d"(dst[2 * p2 + 1])
+                                     : "r"(lk + (unsigned)(k * 32 + 2 * p2) * 8u) : "memory");
+            };
+            load_l(lb[0], 0);
 #pragma unroll
             for (int k = 0; k < 31; ++k) {
+                if (k + 1 < 31) load_l(lb[(k + 1) & 1], k + 1);
                 const double u = __shfl_sync(FULLM, x[k >> 2], ((k & 3) << 3) | cl);
 #pragma unroll
                 for (int i8 = 0; i8 < 8; ++i8) {
                     if (4 * i8 + 3 > k) {
                         const int i = rg + 4 * i8;
-                        const double l = Lk[k * 32 + i];
-                        if (i > k) x[i8] = fma(-l, u, x[i8]);
+                        if (i > k) x[i8] = fma(-lb[k & 1][i8], u, x[i8]);
                     }
                 }
             }

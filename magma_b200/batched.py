@@ -221,6 +221,10 @@ def rcp_selftest(n: int, queue) -> int:
     return _lib.load().magma_b200_rcp_selftest(n, _q(queue))
 
 
+def set_chain_panel(on: int):
+    _lib.load().magma_b200_set_chain_panel(on)
+
+
 def set_fused_max(n: int):
     _lib.load().magma_b200_set_fused_max(n)
 

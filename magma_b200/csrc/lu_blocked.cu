@@ -1802,8 +1802,14 @@ magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, i
         const int j = 32 * J;
         if (j < max_mn) {
             const int T = ((max_m - j + 31) / 32) * 32;
-            launch_panel32(d, dA, dipiv, dinfo, recs, j, T, batch, il, s, sinv, sinv_rows, sinv_blocks, nopiv);
-            MB200_CHECK_LAUNCH("panel_kernel");
+            // single-warp pivot chains (panel_chain_kernel, lu_fused.cu) for the 97..128-row panels: 1.6% on the n = 128 call;
+            // shorter panels stay with panel_kernel, whose 8..12 CTAs per SM beat the chain kernel's 8 (n = 64: 4.36 vs 4.87 ms)
+            if (!nopiv && g_chain_panel && T > 96 && T <= 128) {
+                if ((rc = panel_chain_launch(d, dA, dipiv, dinfo, j, T, batch, il, s, sinv, sinv_rows, sinv_blocks)) != 0) return rc;
+            } else {
+                launch_panel32(d, dA, dipiv, dinfo, recs, j, T, batch, il, s, sinv, sinv_rows, sinv_blocks, nopiv);
+                MB200_CHECK_LAUNCH("panel_kernel");
+            }
             // a last, narrower panel with columns to its right in the same slab (wide matrices). Variable sizes:
             // any panel may be some matrix's last one, the kernel sorts that out per matrix.
             const bool partial_here = d.vm ? (max_n > j + 1) : (max_mn < j + 32 && max_n > max_mn);

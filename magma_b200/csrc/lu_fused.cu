@@ -34,6 +34,7 @@ constexpr int FLDU = 68;   // U block rows: B fragments (k = 4s+q, col 8c+g) con
 constexpr int FLDR = 136;  // staging of the right part, 32 columns: 32*136 = 64*68 doubles >= 64*66
 
 struct FusedSmem {
+    static constexpr int LDU = FLDU;
     double M[64 * FLD];    // left part, column c at M + c*FLD (rows 0..m-1)
     double R[32 * FLDR];   // right part staging (32 columns per round); then -U12 (64 x FLDU); then A22 (64 x FLD2)
     double Un[8 * FLDU];   // -U block row of the current sub-panel step
@@ -165,8 +166,8 @@ __device__ __noinline__ int chain_slow_pick(double v0, double v1, double v2, dou
 // first version's time). The winner's multipliers so far are row i of L11 (S.L11, read by the block-row solve); lane 0
 // stores the pivot row's U part; every live row stores its new multiplier. A pivot row's registers are dead from then
 // on, so the rank-1 update runs on every slot unconditionally (dead and padding slots compute garbage nobody reads).
-template <int NA, int LD>
-__device__ __forceinline__ void panel_chain(FusedSmem &S, const unsigned vbase, const int j, const int jb, const int mv,
+template <int NA, int LD, typename SM>
+__device__ __forceinline__ void panel_chain(SM &S, const unsigned vbase, const int j, const int jb, const int mv,
                                             const int k0, const int lane, const int row_off)
 {
     const unsigned FULL = 0xffffffffu;
@@ -305,10 +306,12 @@ __device__ __forceinline__ void panel_chain(FusedSmem &S, const unsigned vbase, 
 // Warp 0 runs the pivot chains; warps 1..7 apply each finished sub-panel to the view: net row permutation on every
 // column, block row solve, rank-8 DMMA update -- the next sub-panel's eight columns FIRST, so that the chain warp
 // starts on them while the bulk of the update is still running (look-ahead of one sub-panel).
-template <int LD, bool TRACK_PERM>
-__device__ __forceinline__ void factor_view(FusedSmem &S, double *__restrict__ V, const int mv, const int nv, const int row_off,
+template <int LD, bool TRACK_PERM, int NU, typename SM>
+__device__ __forceinline__ void factor_view(SM &S, double *__restrict__ V, const int mv, const int nv, const int row_off,
                                             double *__restrict__ X, const int xcols, const int tid, const int lane, const int w)
 {
+    // NU update warps (warps 1..NU); warp 0 runs the chains. NT threads take part in the hand-over barriers.
+    constexpr int NT = 32 * (NU + 1), NUT = 32 * NU, NH = 2 * NU;
     const int g = lane >> 2, q = lane & 3;
     const int kv = mv < nv ? mv : nv;
     const int tm = (mv + 7) >> 3, tn = (nv + 7) >> 3;
@@ -316,49 +319,49 @@ __device__ __forceinline__ void factor_view(FusedSmem &S, double *__restrict__ V
         const unsigned vbase = f_saddr(V);
         for (int j = 0; j < kv; j += 8) {
             const int jb = (kv - j) < 8 ? (kv - j) : 8;
-            if (j > 0) f_bar_sync(BAR_NEXT, FT);
+            if (j > 0) f_bar_sync(BAR_NEXT, NT);
             const int k0 = j >> 5;
             const int na = ((mv + 31) >> 5) - k0;
-            if (LD == FLD && na >= 4) panel_chain<(LD == FLD ? 4 : 2), LD>(S, vbase, j, jb, mv, k0, lane, row_off);
-            else if (LD == FLD && na == 3) panel_chain<(LD == FLD ? 3 : 2), LD>(S, vbase, j, jb, mv, k0, lane, row_off);
-            else if (na == 2) panel_chain<2, LD>(S, vbase, j, jb, mv, k0, lane, row_off);
+            if (LD > 98 && na >= 4) panel_chain<(LD > 98 ? 4 : 1), LD>(S, vbase, j, jb, mv, k0, lane, row_off);
+            else if (LD > 66 && na == 3) panel_chain<(LD > 66 ? 3 : 1), LD>(S, vbase, j, jb, mv, k0, lane, row_off);
+            else if (LD > 34 && na == 2) panel_chain<(LD > 34 ? 2 : 1), LD>(S, vbase, j, jb, mv, k0, lane, row_off);
             else panel_chain<1, LD>(S, vbase, j, jb, mv, k0, lane, row_off);
             __threadfence_block();
-            f_bar_arrive(BAR_PANEL, FT);
+            f_bar_arrive(BAR_PANEL, NT);
         }
         return;
     }
-    const int wu = w - 1;            // 0..6
-    const int tu = tid - 32;         // 0..223
-    const int hw = tu >> 4;          // half-warp 0..13: owns the columns o = hw, hw + 14, ...
+    const int wu = w - 1;            // 0..NU-1
+    const int tu = tid - 32;         // 0..NUT-1
+    const int hw = tu >> 4;          // half-warp 0..NH-1: owns the columns o = hw, hw + NH, ...
     const int e = lane & 15;
     for (int j = 0; j < kv; j += 8) {
         const int jb = (kv - j) < 8 ? (kv - j) : 8;
-        f_bar_sync(BAR_PANEL, FT);
+        f_bar_sync(BAR_PANEL, NT);
         // ---- the sub-panel's net row permutation on every column of the view (and of X) --------------------------
         const int nmv = S.nmoves;
         if (nmv > 0) {
             const bool eok = e < nmv;
             const int src = eok ? (int)S.msrc[e] : 0, dst = eok ? (int)S.mdst[e] : 0;
             auto apply = [&](double *__restrict__ base, const int ld, const int ncols) {
-                for (int o0 = 0; o0 < ncols; o0 += 14 * 5) {  // warp-uniform trip count: __syncwarp inside
+                for (int o0 = 0; o0 < ncols; o0 += NH * 5) {  // warp-uniform trip count: __syncwarp inside
                     double v[5];
 #pragma unroll
                     for (int u = 0; u < 5; ++u) {
-                        const int o = o0 + hw + 14 * u;
+                        const int o = o0 + hw + NH * u;
                         if (eok && o < ncols) v[u] = base[o * ld + src];
                     }
                     __syncwarp();
 #pragma unroll
                     for (int u = 0; u < 5; ++u) {
-                        const int o = o0 + hw + 14 * u;
+                        const int o = o0 + hw + NH * u;
                         if (eok && o < ncols) base[o * ld + dst] = v[u];
                     }
                 }
             };
             apply(V, LD, nv);
             if (xcols > 0) apply(X, FLD, xcols);
-            if (TRACK_PERM && w == 7) {
+            if (TRACK_PERM && w == NU) {
                 const unsigned char pp = S.perm[src];
                 __syncwarp();
                 if (lane < nmv) S.perm[dst] = pp;
@@ -366,10 +369,10 @@ __device__ __forceinline__ void factor_view(FusedSmem &S, double *__restrict__ V
         }
         const int nright = nv - j - jb;
         if (nright > 0) {
-            f_bar_sync(BAR_MOVED, FT - 32);
+            f_bar_sync(BAR_MOVED, NUT);
             // ---- block row of the columns to the right: U = L11^-1 * (rows j..j+jb-1), one thread per column
-            if (tu < nright) {
-                const int c = j + jb + tu;
+            for (int rc = tu; rc < nright; rc += NUT) {
+                const int c = j + jb + rc;
                 double *col = V + c * LD + j;
                 double x[8];
 #pragma unroll
@@ -384,63 +387,48 @@ __device__ __forceinline__ void factor_view(FusedSmem &S, double *__restrict__ V
                 for (int i = 0; i < 8; ++i) {
                     if (i < jb) {
                         col[i] = x[i];
-                        S.Un[i * FLDU + c] = -x[i];
+                        S.Un[i * SM::LDU + c] = -x[i];
                     }
                 }
             }
         }
-        f_bar_sync(BAR_UPD, FT - 32);
+        f_bar_sync(BAR_UPD, NUT);
         // ---- rows below, columns to the right: C -= L21 * U12 (k = 8: two DMMA per 8x8 tile) ---------------------
         const bool upd = (jb == 8) && (j + 8 < mv) && (j + 8 < nv);
         const int t0 = (j + 8) >> 3;
-        double af[3][2];
         if (upd) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int t = t0 + wu + 7 * r;
-                if (t < tm) {
-                    af[r][0] = V[(j + q) * LD + 8 * t + g];
-                    af[r][1] = V[(j + 4 + q) * LD + 8 * t + g];
-                }
-            }
             // the next sub-panel's columns first
-            {
-                const double bf0 = S.Un[q * FLDU + 8 * t0 + g];
-                const double bf1 = S.Un[(4 + q) * FLDU + 8 * t0 + g];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const int t = t0 + wu + 7 * r;
-                    if (t < tm) {
-                        double *cp = V + (8 * t0 + 2 * q) * LD + 8 * t + g;
-                        double c0 = cp[0], c1 = cp[LD];
-                        f_dmma(c0, c1, af[r][0], bf0);
-                        f_dmma(c0, c1, af[r][1], bf1);
-                        cp[0] = c0;
-                        cp[LD] = c1;
-                    }
-                }
+            const double bf0 = S.Un[q * SM::LDU + 8 * t0 + g];
+            const double bf1 = S.Un[(4 + q) * SM::LDU + 8 * t0 + g];
+            for (int t = t0 + wu; t < tm; t += NU) {
+                const double af0 = V[(j + q) * LD + 8 * t + g];
+                const double af1 = V[(j + 4 + q) * LD + 8 * t + g];
+                double *cp = V + (8 * t0 + 2 * q) * LD + 8 * t + g;
+                double c0 = cp[0], c1 = cp[LD];
+                f_dmma(c0, c1, af0, bf0);
+                f_dmma(c0, c1, af1, bf1);
+                cp[0] = c0;
+                cp[LD] = c1;
             }
         }
         if (j + 8 < kv) {
             __threadfence_block();
-            f_bar_arrive(BAR_NEXT, FT);
+            f_bar_arrive(BAR_NEXT, NT);
         }
-        if (upd) {
+        if (upd && t0 + 1 < tn) {
+            for (int t = t0 + wu; t < tm; t += NU) {
+                const double af0 = V[(j + q) * LD + 8 * t + g];
+                const double af1 = V[(j + 4 + q) * LD + 8 * t + g];
 #pragma unroll 2
-            for (int ct = t0 + 1; ct < tn; ++ct) {
-                const double bf0 = S.Un[q * FLDU + 8 * ct + g];
-                const double bf1 = S.Un[(4 + q) * FLDU + 8 * ct + g];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const int t = t0 + wu + 7 * r;
-                    if (t < tm) {
-                        double *cp = V + (8 * ct + 2 * q) * LD + 8 * t + g;
-                        double c0 = cp[0], c1 = cp[LD];
-                        f_dmma(c0, c1, af[r][0], bf0);
-                        f_dmma(c0, c1, af[r][1], bf1);
-                        cp[0] = c0;
-                        cp[LD] = c1;
-                    }
+                for (int ct = t0 + 1; ct < tn; ++ct) {
+                    const double bf0 = S.Un[q * SM::LDU + 8 * ct + g];
+                    const double bf1 = S.Un[(4 + q) * SM::LDU + 8 * ct + g];
+                    double *cp = V + (8 * ct + 2 * q) * LD + 8 * t + g;
+                    double c0 = cp[0], c1 = cp[LD];
+                    f_dmma(c0, c1, af0, bf0);
+                    f_dmma(c0, c1, af1, bf1);
+                    cp[0] = c0;
+                    cp[LD] = c1;
                 }
             }
         }
@@ -502,7 +490,7 @@ lu_fused_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int 
     }
 
     // ---- left part ---------------------------------------------------------------------------------------------
-    factor_view<FLD, true>(S, S.M, m, nl, 0, nullptr, 0, tid, lane, w);
+    factor_view<FLD, true, 7>(S, S.M, m, nl, 0, nullptr, 0, tid, lane, w);
     __syncthreads();
 
     // ---- right part --------------------------------------------------------------------------------------------
@@ -620,7 +608,7 @@ lu_fused_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int 
                 A22[(8 * ct + 2 * q + 1) * FLD2 + 8 * w + g] = acc[1][ct][1];
             }
             __syncthreads();
-            factor_view<FLD2, false>(S, A22, m - 64, nr, 64, S.M + 64, 64, tid, lane, w);
+            factor_view<FLD2, false, 7>(S, A22, m - 64, nr, 64, S.M + 64, 64, tid, lane, w);
             __syncthreads();
         }
     }
@@ -649,6 +637,92 @@ lu_fused_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int 
         for (int i = tid; i < mn; i += FT) dipiv[b][i] = S.ipiv[i] + 1;
         if (tid == 0) dinfo[b] = S.info;
     }
+}
+
+// ---- 32-column panel of the left-looking slab driver, panels of at most 128 rows ------------------------------------
+// Replaces panel_kernel (lu_blocked.cu: one thread per row, two block barriers and two arg-max cascades per column,
+// ~21k warp-instructions per 128 x 32 panel, 54% issue-slot utilisation) for short panels: the slab's rows j.. arrive
+// by TMA in shared memory, ONE warp runs the pivot chains of the four 8-column sub-panels, a second warp applies each
+// finished sub-panel to the rest of the slab (permutation, block-row solve, rank-8 DMMA update; next sub-panel first).
+// Two warps and LD*256 bytes per CTA: 6 (128 rows) .. 16 (32 rows) pivot chains per SM.
+// Outputs as panel_kernel's: factors in final row order, global pivots, info, and the step permutation record sinv.
+template <int LD>
+struct PanelSmem {
+    static constexpr int LDU = 36;  // 32 columns (+4: B fragments conflict-free)
+    double V[32 * LD];
+    double Un[8 * LDU];
+    double L11[64];
+    unsigned long long bar[1];
+    int ipiv[128];
+    int nmoves;
+    int info;
+    unsigned char mdst[16], msrc[16];
+    unsigned char perm[128];  // row at panel position p now = panel row perm[p] before the panel
+};
+
+template <int LD, int MINB>
+__global__ void __launch_bounds__(64, MINB)
+panel_chain_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__restrict__ dinfo, int j, long batch,
+                   const int *__restrict__ index_list, unsigned short *__restrict__ sinv, int sinv_rows, int sinv_blocks)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PanelSmem<LD> &S = *reinterpret_cast<PanelSmem<LD> *>(smem_raw);
+    const long slot = blockIdx.x;
+    const long b = index_list ? index_list[slot] : slot;
+    if (b < 0) return;
+    int m, n, ld;
+    dims_of(d, b, m, n, ld);
+    const int mn = m < n ? m : n;
+    if (j >= mn) return;
+    const int jb = (mn - j) < 32 ? (mn - j) : 32;
+    const int mp = m - j;  // <= LD - 2
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    double *__restrict__ A = dA[b] + (size_t)j + (size_t)j * ld;  // panel origin
+    const bool bulk = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((ld & 1) == 0) && ((mp & 1) == 0);
+    const unsigned colbytes = (unsigned)mp * 8u;
+    if (tid == 0) {
+        f_mbar_init(&S.bar[0], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.info = 0;
+        S.nmoves = 0;
+    }
+    for (int i = tid; i < 128; i += 64) S.perm[i] = (unsigned char)i;
+    __syncthreads();
+    if (bulk) {
+        if (w == 0) {
+            if (lane == 0) f_mbar_expect(&S.bar[0], colbytes * (unsigned)jb);
+            __syncwarp();
+            if (lane < jb) f_bulk_load(&S.V[lane * LD], A + (size_t)lane * ld, colbytes, &S.bar[0]);
+        }
+        f_mbar_wait(&S.bar[0], 0);
+    } else {
+        for (int c = w; c < jb; c += 2)
+            for (int r = lane; r < mp; r += 32) S.V[c * LD + r] = A[r + (size_t)c * ld];
+        __syncthreads();
+    }
+    // S.ipiv / S.info are panel-relative here (row_off = 0): j is added on the way out
+    factor_view<LD, true, 1>(S, S.V, mp, jb, 0, nullptr, 0, tid, lane, w);
+    __syncthreads();
+    if (bulk) {
+        f_fence_async_smem();
+        __syncthreads();
+        if (w == 0 && lane < jb) f_bulk_store(A + (size_t)lane * ld, &S.V[lane * LD], colbytes);
+    } else {
+        for (int c = w; c < jb; c += 2)
+            for (int r = lane; r < mp; r += 32) A[r + (size_t)c * ld] = S.V[c * LD + r];
+    }
+    if (tid < jb) dipiv[b][j + tid] = j + S.ipiv[tid] + 1;
+    if (sinv) {
+        unsigned short *sv = sinv + ((size_t)slot * sinv_blocks + (j >> 5)) * sinv_rows + j;
+        for (int p = tid; p < mp; p += 64) sv[p] = (unsigned short)(j + S.perm[p]);
+    }
+    if (tid == 0) {
+        const int info = S.info ? j + S.info : 0;
+        if (j == 0) dinfo[b] = info;
+        else if (info && dinfo[b] == 0) dinfo[b] = info;
+    }
+    if (bulk && w == 0) f_bulk_commit_wait();
 }
 
 __global__ void rcp_selftest_kernel(long n, unsigned long long seed, unsigned long long *bad)
@@ -682,6 +756,28 @@ long rcp_selftest_run(long n, cudaStream_t s)
     cudaStreamSynchronize(s);
     cudaFree(d);
     return cudaGetLastError() == cudaSuccess ? (long)h : -1;
+}
+
+// 32-column panel at (j, j) of matrices with at most 128 rows below j; T = roundup(rows, 32). -100: not covered.
+magma_int_t panel_chain_launch(const Dims &d, double **dA, int **dipiv, int *dinfo, int j, int T, long batch, const int *il,
+                               cudaStream_t s, unsigned short *sinv, int sinv_rows, int sinv_blocks)
+{
+    if (T > 128 || batch <= 0) return -100;
+#define MB200_PC(LD_, MINB_)                                                                                              \
+    do {                                                                                                                  \
+        static DevOnce once;                                                                                              \
+        smem_optin(once, panel_chain_kernel<LD_, MINB_>, sizeof(PanelSmem<LD_>));                                         \
+        panel_chain_kernel<LD_, MINB_><<<(unsigned)batch, 64, sizeof(PanelSmem<LD_>), s>>>(d, dA, dipiv, dinfo, j, batch, il, \
+                                                                                          sinv, sinv_rows, sinv_blocks); \
+    } while (0)
+    if (T <= 32) MB200_PC(34, 8);
+    else if (T <= 64) MB200_PC(66, 8);
+    else if (T <= 96) MB200_PC(98, 8);
+    else MB200_PC(130, 6);
+#undef MB200_PC
+    count_launch();
+    MB200_CHECK_LAUNCH("panel_chain_kernel");
+    return 0;
 }
 
 magma_int_t lu_fused_launch(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo, long batch,

@@ -10,6 +10,7 @@
 namespace mb200 {
 std::atomic<int64_t> g_launches{0};
 int g_tier = 0;
+int g_chain_panel = 1;
 static std::atomic<int> g_init_count{0};
 
 #ifdef MB200_INTERPOSE
@@ -452,4 +453,5 @@ extern "C" {
 int64_t magma_b200_launch_count(void) { return g_launches.load(); }
 void magma_b200_set_tier(int tier) { g_tier = tier; }
 void magma_b200_set_small_rows(int rows) { g_small_rows = rows; }
+void magma_b200_set_chain_panel(int on) { g_chain_panel = on; }
 }  // extern "C"

@@ -6,6 +6,7 @@ from magma_b200 import batched as mb
 n, batch = int(sys.argv[1]), int(sys.argv[2]); reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 torch.cuda.set_device(0); mb.magma_init(); q = mb.Queue.from_torch(0)
 if os.environ.get("FUSED_MAX"): mb.set_fused_max(int(os.environ["FUSED_MAX"]))
+if os.environ.get("CHAIN_PANEL"): mb.set_chain_panel(int(os.environ["CHAIN_PANEL"]))
 db = mb.DeviceBatch(batch, n, n, queue=q)
 seed = np.array([0, 0, 0, 1], dtype=np.int32)
 mb.dlarnv_uniform(seed, batch * n * n, db.A, q); q.sync(); A0 = db.A.clone()

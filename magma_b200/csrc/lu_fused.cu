@@ -758,23 +758,15 @@ long rcp_selftest_run(long n, cudaStream_t s)
     return cudaGetLastError() == cudaSuccess ? (long)h : -1;
 }
 
-// 32-column panel at (j, j) of matrices with at most 128 rows below j; T = roundup(rows, 32). -100: not covered.
+// 32-column panel at (j, j) of matrices with 97..128 rows below j; T = roundup(rows, 32). -100: not covered.
 magma_int_t panel_chain_launch(const Dims &d, double **dA, int **dipiv, int *dinfo, int j, int T, long batch, const int *il,
                                cudaStream_t s, unsigned short *sinv, int sinv_rows, int sinv_blocks)
 {
-    if (T > 128 || batch <= 0) return -100;
-#define MB200_PC(LD_, MINB_)                                                                                              \
-    do {                                                                                                                  \
-        static DevOnce once;                                                                                              \
-        smem_optin(once, panel_chain_kernel<LD_, MINB_>, sizeof(PanelSmem<LD_>));                                         \
-        panel_chain_kernel<LD_, MINB_><<<(unsigned)batch, 64, sizeof(PanelSmem<LD_>), s>>>(d, dA, dipiv, dinfo, j, batch, il, \
-                                                                                          sinv, sinv_rows, sinv_blocks); \
-    } while (0)
-    if (T <= 32) MB200_PC(34, 8);
-    else if (T <= 64) MB200_PC(66, 8);
-    else if (T <= 96) MB200_PC(98, 8);
-    else MB200_PC(130, 6);
-#undef MB200_PC
+    if (T <= 96 || T > 128 || batch <= 0) return -100;  // shorter panels: panel_kernel's higher occupancy wins (lu_blocked.cu)
+    static DevOnce once;
+    smem_optin(once, panel_chain_kernel<130, 6>, sizeof(PanelSmem<130>));
+    panel_chain_kernel<130, 6><<<(unsigned)batch, 64, sizeof(PanelSmem<130>), s>>>(d, dA, dipiv, dinfo, j, batch, il, sinv, sinv_rows,
+                                                                                 sinv_blocks);
     count_launch();
     MB200_CHECK_LAUNCH("panel_chain_kernel");
     return 0;

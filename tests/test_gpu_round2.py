@@ -80,6 +80,27 @@ def test_fused_tier_full_size_sample(gpu_queue, fused_tier):
     check_against_oracle(gpu_queue, A0, n)
 
 
+@pytest.mark.parametrize("chain", [0, 1])
+@pytest.mark.parametrize("m,n,batch", [(128, 128, 7), (100, 100, 5), (97, 97, 5), (128, 40, 5), (120, 200, 4), (127, 96, 4), (226, 130, 3)])
+def test_chain_panel_switch(gpu_queue, chain, m, n, batch):
+    """Panels of 97..128 rows: single-warp chain kernel (default) and the one-thread-per-row kernel give the same bits."""
+    mb.set_chain_panel(chain)
+    try:
+        A0, _ = oracle.random_batch(batch, m, n)
+        check_against_oracle(gpu_queue, A0, m)
+    finally:
+        mb.set_chain_panel(1)
+
+
+def test_chain_panel_structured(gpu_queue):
+    rng = np.random.default_rng(9)
+    n = 128
+    mats = [np.zeros((n, n)), np.ones((n, n)), np.eye(n), np.fliplr(np.eye(n)), rng.integers(-3, 4, size=(n, n)).astype(float)]
+    Z = rng.random((n, n)); Z[:, 5] = 0.0; Z[:, 100] = 0.0; mats.append(Z)
+    Z2 = rng.random((n, n)); Z2[n // 2:, :] = Z2[:n - n // 2, :]; mats.append(Z2)
+    check_against_oracle(gpu_queue, np.stack(mats), n)
+
+
 # ---- source-compatibility entry points ---------------------------------------------------------------------------
 
 def _panel_case(q, fn_name, m, n, ai, batch=5, M=150, N=70):

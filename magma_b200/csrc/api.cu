@@ -357,18 +357,21 @@ static size_t vbatched_base_bytes(long batch)
 {
     return (vbatched_lists_bytes(batch) + lu_blocked_workspace_bytes(batch) + 255) & ~(size_t)255;
 }
-static size_t vbatched_perm_bytes(long batch)
+// int_cap: the caller-provided workspace of magma_dgetrf_vbatched_max_nocheck_work is sized through an int (lwork), so
+// there the step-permutation records are dropped once the total no longer fits; the entries that use queue scratch have
+// no such limit and always keep the left-looking driver.
+static size_t vbatched_perm_bytes(long batch, bool int_cap)
 {
     const size_t p = lu_blocked_perm_bytes(batch, 512, 512);
-    return (vbatched_base_bytes(batch) + p <= 0x7fffff00ull) ? p : 0;
+    return (!int_cap || vbatched_base_bytes(batch) + p <= 0x7fffff00ull) ? p : 0;
 }
-static size_t vbatched_work_bytes(long batch) { return vbatched_base_bytes(batch) + vbatched_perm_bytes(batch); }
+static size_t vbatched_work_bytes(long batch, bool int_cap) { return vbatched_base_bytes(batch) + vbatched_perm_bytes(batch, int_cap); }
 
 // known[c] >= 0: size of bin c (read back by the synchronous driver); < 0: unknown (asynchronous expert
 // entries: every list is pre-filled with -1 and launched over `batch` slots, CTAs that draw -1 exit).
 static magma_int_t vbatched_run(magma_int_t *m, magma_int_t *n, int max_m, int max_n, double **dA_array,
                                 magma_int_t *ldda, magma_int_t **ipiv_array, magma_int_t *info_array, void *work,
-                                long batch, magma_queue_t queue, const int *known)
+                                long batch, magma_queue_t queue, const int *known, bool int_cap)
 {
     cudaStream_t s = MB200_Q(queue)->stream;
     Dims d;
@@ -397,7 +400,7 @@ static magma_int_t vbatched_run(magma_int_t *m, magma_int_t *n, int max_m, int m
         else rc = lu_blocked_launch(d, 32, 32, dA_array, ipiv_array, info_array, cnt[0], lists, recs, s);
     }
     static const int cap[3] = {64, 96, 128};
-    void *perm = vbatched_perm_bytes(batch) ? (char *)work + vbatched_base_bytes(batch) : nullptr;
+    void *perm = vbatched_perm_bytes(batch, int_cap) ? (char *)work + vbatched_base_bytes(batch) : nullptr;
     for (int c = 1; c <= 3 && rc == 0; ++c)
         if (cnt[c] > 0) {
             rc = lu_mid_launch(d, imin(max_m, cap[c - 1]), imin(max_n, cap[c - 1]), dA_array, ipiv_array, info_array,
@@ -422,7 +425,11 @@ magma_int_t magma_dgetrf_vbatched_max_nocheck_work(magma_int_t *m, magma_int_t *
                                                    magma_int_t batchCount, magma_queue_t queue)
 {
     (void)max_minmn; (void)max_mxn;
-    const size_t need = vbatched_work_bytes(batchCount);
+    const size_t need = vbatched_work_bytes(batchCount, true);
+    if (need > 0x7fffffffull) {  // even the index lists and pivot records do not fit an int-sized lwork: say so
+        magma_xerbla(__func__, 13);
+        return -13;
+    }
     if (lwork[0] < 0) {  // workspace query (src/zgetrf_vbatched.cpp:257-261)
         lwork[0] = (magma_int_t)need;
         return 0;
@@ -432,7 +439,7 @@ magma_int_t magma_dgetrf_vbatched_max_nocheck_work(magma_int_t *m, magma_int_t *
         return -12;
     }
     if (batchCount <= 0 || max_m == 0 || max_n == 0) return 0;
-    return vbatched_run(m, n, max_m, max_n, dA_array, ldda, dipiv_array, info_array, work, batchCount, queue, nullptr);
+    return vbatched_run(m, n, max_m, max_n, dA_array, ldda, dipiv_array, info_array, work, batchCount, queue, nullptr, true);
 }
 
 magma_int_t magma_dgetrf_vbatched_max_nocheck(magma_int_t *m, magma_int_t *n, magma_int_t *minmn, magma_int_t max_m,
@@ -443,12 +450,12 @@ magma_int_t magma_dgetrf_vbatched_max_nocheck(magma_int_t *m, magma_int_t *n, ma
 {
     (void)minmn; (void)max_minmn; (void)max_mxn; (void)nb; (void)recnb; (void)pivinfo_array;
     if (batchCount <= 0 || max_m == 0 || max_n == 0) return 0;
-    void *work = queue_dscratch(queue, vbatched_work_bytes(batchCount));
+    void *work = queue_dscratch(queue, vbatched_work_bytes(batchCount, false));
     if (!work) {
         magma_xerbla(__func__, -MAGMA_ERR_DEVICE_ALLOC);
         return MAGMA_ERR_DEVICE_ALLOC;
     }
-    return vbatched_run(m, n, max_m, max_n, dA_array, ldda, ipiv_array, info_array, work, batchCount, queue, nullptr);
+    return vbatched_run(m, n, max_m, max_n, dA_array, ldda, ipiv_array, info_array, work, batchCount, queue, nullptr, false);
 }
 
 magma_int_t magma_dgetrf_vbatched(magma_int_t *m, magma_int_t *n, double **dA_array, magma_int_t *ldda,
@@ -461,7 +468,7 @@ magma_int_t magma_dgetrf_vbatched(magma_int_t *m, magma_int_t *n, double **dA_ar
     }
     if (batchCount == 0) return 0;
     // one statistics kernel + one D2H read (the reference: checker kernel + read, setup kernel + read)
-    char *scr = (char *)queue_dscratch(queue, vbatched_work_bytes(batchCount) + 64);  // 64: the statistics block
+    char *scr = (char *)queue_dscratch(queue, vbatched_work_bytes(batchCount, false) + 64);  // 64: the statistics block
     if (!scr) {
         magma_xerbla(__func__, -MAGMA_ERR_DEVICE_ALLOC);
         return MAGMA_ERR_DEVICE_ALLOC;
@@ -491,7 +498,7 @@ magma_int_t magma_dgetrf_vbatched(magma_int_t *m, magma_int_t *n, double **dA_ar
     if (mid_max < 128) { known[4] += known[3]; known[3] = 0; }
     known[6] = h[6] - known[0] - known[1] - known[2] - known[3] - known[4] - known[5];
     magma_int_t rc = vbatched_run(m, n, max_m, max_n, dA_array, ldda, ipiv_array, info_array, work, batchCount, queue,
-                                  known);
+                                  known, false);
     // the reference's driver returns after a queue sync (src/zgetrf_vbatched.cpp:392)
     cudaStreamSynchronize(MB200_Q(queue)->stream);
     return rc;

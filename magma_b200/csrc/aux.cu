@@ -237,6 +237,7 @@ void identity_launch(int n, double **dB, int lddb, long batch, cudaStream_t s)
         const long cnt = batch - off < 65535 ? batch - off : 65535;
         identity_kernel<<<dim3((unsigned)gx, (unsigned)cnt), 256, 0, s>>>(n, dB + off, lddb, cnt);
         count_launch();
+        MB200_CHECK_LAUNCH_VOID("identity_kernel");
     }
 }
 

@@ -569,9 +569,13 @@ void laswp_rowserial_launch(int n, double **dA, int lda, int k1, int k2, int **d
     if (n <= 0 || batch <= 0 || k2 < k1) return;
     const int threads = n < 128 ? ((n + 31) / 32) * 32 : 128;
     const int col_tiles = (n + threads - 1) / threads;
-    laswp_rowserial_kernel<<<(unsigned)(batch * col_tiles), threads, 0, s>>>(n, dA, lda, k1, k2, dipiv, col_tiles);
-    count_launch();
-    MB200_CHECK_LAUNCH_VOID("laswp_rowserial_kernel");
+    const long per = 0x7fffffffL / col_tiles;  // grid.x stays below 2^31: larger batches go in chunks
+    for (long off = 0; off < batch; off += per) {
+        const long cnt = batch - off < per ? batch - off : per;
+        laswp_rowserial_kernel<<<(unsigned)(cnt * col_tiles), threads, 0, s>>>(n, dA + off, lda, k1, k2, dipiv + off, col_tiles);
+        count_launch();
+        MB200_CHECK_LAUNCH_VOID("laswp_rowserial_kernel");
+    }
 }
 
 void trsm_left_launch(int uplo, int trans, int diag, int m, int n, double alpha, double **dA, int ldda,
@@ -582,15 +586,20 @@ void trsm_left_launch(int uplo, int trans, int diag, int m, int n, double alpha,
     const int tr = pick_tr(m, n, smem);
     if (tr == 0) {
         fprintf(stderr, "libmagma_b200: magmablas_dtrsm_batched: m = %d too large for the shared-memory solver\n", m);
+        magma_xerbla("magmablas_dtrsm_batched", -MAGMA_ERR_NOT_SUPPORTED);
         return;
     }
     const int rhs_tiles = (n + tr - 1) / tr;
     static DevOnce once;
     smem_optin(once, trsm_left_kernel, 227 * 1024);
-    trsm_left_kernel<<<(unsigned)(batch * rhs_tiles), SOLVE_THREADS, smem, s>>>(uplo, trans, diag, m, n, tr, alpha, dA,
-                                                                              ldda, dB, lddb, rhs_tiles);
-    count_launch();
-    MB200_CHECK_LAUNCH_VOID("trsm_left_kernel");
+    const long per = 0x7fffffffL / rhs_tiles;
+    for (long off = 0; off < batch; off += per) {
+        const long cnt = batch - off < per ? batch - off : per;
+        trsm_left_kernel<<<(unsigned)(cnt * rhs_tiles), SOLVE_THREADS, smem, s>>>(uplo, trans, diag, m, n, tr, alpha, dA + off,
+                                                                                ldda, dB + off, lddb, rhs_tiles);
+        count_launch();
+        MB200_CHECK_LAUNCH_VOID("trsm_left_kernel");
+    }
 }
 
 void gemm_nn_launch(int m, int n, int k, double alpha, double const *const *dA, int Ai, int Aj, int ldda,
@@ -599,10 +608,14 @@ void gemm_nn_launch(int m, int n, int k, double alpha, double const *const *dA, 
 {
     if (m <= 0 || n <= 0 || batch <= 0) return;
     const int mt = (m + 31) / 32, nt = (n + 31) / 32;
-    gemm_nn_kernel<<<(unsigned)(batch * mt * nt), 256, 0, s>>>(m, n, k, alpha, dA, Ai, Aj, ldda, dB, Bi, Bj, lddb,
-                                                             beta, dC, Ci, Cj, lddc, mt, nt);
-    count_launch();
-    MB200_CHECK_LAUNCH_VOID("gemm_nn_kernel");
+    const long per = 0x7fffffffL / ((long)mt * nt);
+    for (long off = 0; off < batch; off += per) {
+        const long cnt = batch - off < per ? batch - off : per;
+        gemm_nn_kernel<<<(unsigned)(cnt * mt * nt), 256, 0, s>>>(m, n, k, alpha, dA + off, Ai, Aj, ldda, dB + off, Bi, Bj, lddb,
+                                                               beta, dC + off, Ci, Cj, lddc, mt, nt);
+        count_launch();
+        MB200_CHECK_LAUNCH_VOID("gemm_nn_kernel");
+    }
 }
 
 }  // namespace mb200

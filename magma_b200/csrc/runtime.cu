@@ -36,6 +36,10 @@ void *queue_dscratch(magma_queue_t queue, size_t bytes, int slot)
 {
     auto *q = MB200_Q(queue);
     if (q->dscratch_bytes[slot] < bytes) {
+        // the scratch belongs to the queue's device, whatever device is current
+        int prev = 0;
+        cudaGetDevice(&prev);
+        if (prev != q->device) cudaSetDevice(q->device);
         if (q->dscratch[slot]) {
             cudaStreamSynchronize(q->stream);
             cudaFree(q->dscratch[slot]);
@@ -43,7 +47,9 @@ void *queue_dscratch(magma_queue_t queue, size_t bytes, int slot)
         q->dscratch[slot] = nullptr;
         q->dscratch_bytes[slot] = 0;
         size_t want = bytes + bytes / 4;
-        if (cudaMalloc(&q->dscratch[slot], want) != cudaSuccess) {
+        const cudaError_t e = cudaMalloc(&q->dscratch[slot], want);
+        if (prev != q->device) cudaSetDevice(prev);
+        if (e != cudaSuccess) {
             cudaGetLastError();
             return nullptr;
         }

@@ -394,9 +394,9 @@ void magma_b200_set_tier(int tier);
 magma_int_t magma_b200_get_dgetrf_batched_crossover(magma_int_t which);
 /* Self-test of the inline reciprocal of lu_fused.cu: mismatches against IEEE 1.0/x over n pseudo-random inputs (0 expected). */
 int64_t magma_b200_rcp_selftest(int64_t n, magma_queue_t queue);
-/* 1 (default): 32-column panels of at most 128 rows run on single-warp pivot chains (panel_chain_kernel); 0: the
- * one-thread-per-row panel kernel everywhere (A/B runs). */
-void magma_b200_set_chain_panel(int on);
+/* Level L = 1..4: 32-column panels of (128 - 32 L, 128] rows run on single-warp pivot chains (panel_chain_kernel);
+ * default 3 (33..128 rows). 0: the one-thread-per-row panel kernel everywhere (A/B runs). */
+void magma_b200_set_chain_panel(int level);
 /* Largest max(m,n) routed to the single-launch shared-memory tier (lu_fused.cu), 0..128; 0 disables it (A/B runs). */
 void magma_b200_set_fused_max(int n);
 /* Largest max(m,n) routed to the register-file tier (lu_mid.cu), 32..128; for tuning sweeps. */

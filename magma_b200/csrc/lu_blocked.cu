@@ -1802,9 +1802,10 @@ magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, i
         const int j = 32 * J;
         if (j < max_mn) {
             const int T = ((max_m - j + 31) / 32) * 32;
-            // single-warp pivot chains (panel_chain_kernel, lu_fused.cu) for the 97..128-row panels: 1.6% on the n = 128 call;
-            // shorter panels stay with panel_kernel, whose 8..12 CTAs per SM beat the chain kernel's 8 (n = 64: 4.36 vs 4.87 ms)
-            if (!nopiv && g_chain_panel && T > 96 && T <= 128) {
+            // single-warp pivot chains (panel_chain_kernel, lu_fused.cu) for panels of 33..128 rows (g_chain_panel = 3: rows >
+            // 128 - 32 * level). Same box, panel_kernel -> chain kernel: n = 128 9.72 -> 9.11 ms, n = 96 5.28 -> 5.00,
+            // n = 64 4.36 -> 4.25, n = 48 3.79 -> 3.66. The last <= 32-row panel stays with panel_kernel (level 4 costs 0.2-0.4 ms).
+            if (!nopiv && T <= 128 && g_chain_panel > 0 && T > 128 - 32 * g_chain_panel) {
                 if ((rc = panel_chain_launch(d, dA, dipiv, dinfo, j, T, batch, il, s, sinv, sinv_rows, sinv_blocks)) != 0) return rc;
             } else {
                 launch_panel32(d, dA, dipiv, dinfo, recs, j, T, batch, il, s, sinv, sinv_rows, sinv_blocks, nopiv);

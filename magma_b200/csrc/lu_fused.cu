@@ -300,12 +300,165 @@ __device__ __forceinline__ void panel_chain(SM &S, const unsigned vbase, const i
     }
 }
 
+// ---- the same sub-panel chain with a ROLLED column loop ----------------------------------------------------------------
+// The unrolled version above is ~1000 straight-line instructions per sub-panel, executed once: ncu charged 40% of the chain
+// warp's time to instruction fetch (`no_instruction`). Here the current column is always register column 0: the rank-1
+// update writes column c into column c-1 (`a[k][c-1] = fma(-l, u[c], a[k][c])` -- the shift is free), so one loop body of
+// ~170 instructions serves every column and stays in the instruction cache. Columns past the live window hold garbage that
+// only ever shifts towards dead columns. The multipliers of the pivot rows (the 8x8 unit-lower block the block-row solve
+// needs) are read from the image after the permutation has been applied, so S.L11 is not used on this path.
+template <int NA, int LD, typename SM>
+__device__ __forceinline__ void panel_chain_rolled(SM &S, const unsigned vbase, const int j, const int jb, const int mv,
+                                                   const int k0, const int lane, const int row_off)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned sip = f_saddr(S.ipiv), smd = f_saddr(S.mdst), sms = f_saddr(S.msrc);
+    unsigned cbase = vbase + (unsigned)(j * LD) * 8u;  // column j + i of the view (advances with i)
+    double a[NA][8];
+    int pos[NA];
+    unsigned alive = 0;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+        const int r = lane + 32 * (k0 + k);
+        const bool valid = (r >= j) && (r < mv);
+        pos[k] = r;
+        alive |= valid ? (1u << k) : 0u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a[k][c] = (valid && c < jb) ? f_lds(cbase + (unsigned)(c * LD + r) * 8u) : 0.0;
+    }
+    const bool lane0 = lane == 0;
+    const unsigned rowb = (unsigned)(lane + 32 * k0) * 8u;  // byte offset of this lane's slot-0 row inside a column
+    int info = 0;
+    int cnt = 0;
+    double u[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+    for (int i = 0; i < jb; ++i) {
+        const int ji = j + i;
+        const int nlive = jb - i;  // live register columns: 0 .. nlive-1
+        unsigned hv[NA];
+        unsigned lmx = 0;
+#pragma unroll
+        for (int k = 0; k < NA; ++k) {
+            hv[k] = ((alive >> k) & 1u) ? ((unsigned)__double2hiint(a[k][0]) & 0x7fffffffu) : 0u;
+            lmx = hv[k] > lmx ? hv[k] : lmx;
+        }
+        const unsigned mx = __reduce_max_sync(FULL, lmx);
+        unsigned code = 0;
+        double cv = 1.0;
+        int lp = 0;
+#pragma unroll
+        for (int k = 0; k < NA; ++k) {
+            const bool hit = hv[k] == mx;
+            code += hit ? (1u << (8 * k)) : 0u;
+            cv = f_sel(hit, a[k][0], cv);
+            lp = hit ? pos[k] : lp;
+        }
+        const double rinv = rcp_fast_f64(cv);
+        asm volatile("" ::"d"(rinv));
+        const unsigned tot = __reduce_add_sync(FULL, code);
+        int wl, K;
+        const bool unique = (mx != 0u) && ((tot & 0xfefefefeu) == 0u) && (__popc(tot) == 1);
+        if (unique) {
+            K = (__ffs(tot) - 1) >> 3;
+            wl = __ffs(__ballot_sync(FULL, code != 0u)) - 1;
+        } else {
+            const int pk = chain_slow_pick(a[0][0], NA > 1 ? a[NA > 1 ? 1 : 0][0] : 0.0, NA > 2 ? a[NA > 2 ? 2 : 0][0] : 0.0,
+                                           NA > 3 ? a[NA > 3 ? 3 : 0][0] : 0.0, pos[0], NA > 1 ? pos[NA > 1 ? 1 : 0] : 0,
+                                           NA > 2 ? pos[NA > 2 ? 2 : 0] : 0, NA > 3 ? pos[NA > 3 ? 3 : 0] : 0, alive);
+            wl = pk & 0xff;
+            K = pk >> 8;
+            lp = pos[0];
+#pragma unroll
+            for (int k = 1; k < NA; ++k) lp = (K == k) ? pos[k] : lp;
+        }
+        const int wp = __shfl_sync(FULL, lp, wl);
+        const bool me = lane == wl;
+#pragma unroll
+        for (int k = 0; k < NA; ++k) pos[k] = (pos[k] == ji) ? wp : pos[k];
+        auto take = [&](auto Kc) {
+            constexpr int KK = decltype(Kc)::value;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) u[c] = __shfl_sync(FULL, a[KK][c], wl);
+            if (nlive > 4) {  // warp-uniform: the second half of the window is dead from column 4 on
+#pragma unroll
+                for (int c = 4; c < 8; ++c) u[c] = __shfl_sync(FULL, a[KK][c], wl);
+            }
+            pos[KK] = me ? ji : pos[KK];
+            alive = me ? (alive & ~(1u << KK)) : alive;
+        };
+        if (NA == 1 || K == 0) take(std::integral_constant<int, 0>{});
+        else if (NA == 2 || K == 1) take(std::integral_constant<int, (NA > 1 ? 1 : 0)>{});
+        else if (NA == 3 || K == 2) take(std::integral_constant<int, (NA > 2 ? 2 : 0)>{});
+        else take(std::integral_constant<int, (NA > 3 ? 3 : 0)>{});
+        double rv;
+        if (unique && mx >= 0x01800000u && mx < 0x7e000000u) {
+            rv = __shfl_sync(FULL, rinv, wl);
+        } else {
+            rv = 1.0 / u[0];
+        }
+        const int prow = wl + 32 * (k0 + K);
+        // lane 0: the pivot row's U part into the image (its physical row), pivot index, its move
+        const unsigned prow_a = cbase + (unsigned)prow * 8u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f_sts_if(lane0 && c < nlive, prow_a + (unsigned)(c * LD) * 8u, u[c]);
+        f_sts32_if(lane0, sip + (unsigned)(row_off + ji) * 4u, row_off + wp);
+        f_sts8_if(lane0 && prow != ji, smd + (unsigned)cnt, ji);
+        f_sts8_if(lane0 && prow != ji, sms + (unsigned)cnt, prow);
+        cnt += (prow != ji) ? 1 : 0;
+        if (u[0] != 0.0) {  // warp-uniform
+            double l[NA];
+#pragma unroll
+            for (int k = 0; k < NA; ++k) {
+                l[k] = a[k][0] * rv;
+                f_sts_if((alive >> k) & 1u, cbase + rowb + (unsigned)(32 * k) * 8u, l[k]);  // column ji of a live row is final
+#pragma unroll
+                for (int c = 1; c < 5; ++c) a[k][c - 1] = fma(-l[k], u[c], a[k][c]);
+            }
+            if (nlive > 5) {  // warp-uniform: columns 5..7 are live only in the first three steps
+#pragma unroll
+                for (int k = 0; k < NA; ++k)
+#pragma unroll
+                    for (int c = 5; c < 8; ++c) a[k][c - 1] = fma(-l[k], u[c], a[k][c]);
+            }
+        } else {
+            if (info == 0) info = row_off + ji + 1;
+#pragma unroll
+            for (int k = 0; k < NA; ++k) {
+                f_sts_if((alive >> k) & 1u, cbase + rowb + (unsigned)(32 * k) * 8u, a[k][0]);  // unscaled, as the oracle leaves it
+#pragma unroll
+                for (int c = 1; c < 8; ++c) a[k][c - 1] = a[k][c];
+            }
+        }
+        cbase += (unsigned)LD * 8u;
+    }
+    // rows that were never a pivot but were displaced join the list
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+        const int r = lane + 32 * (k0 + k);
+        const bool moved = ((alive >> k) & 1u) && pos[k] != r;
+        const unsigned mask = __ballot_sync(FULL, moved);
+        if (moved) {
+            const int idx = cnt + __popc(mask & ((1u << lane) - 1u));
+            S.mdst[idx] = (unsigned char)pos[k];
+            S.msrc[idx] = (unsigned char)r;
+        }
+        cnt += __popc(mask);
+    }
+    if (lane == 0) {
+        S.nmoves = cnt;
+        if (info != 0 && S.info == 0) S.info = info;
+    }
+}
+
 // ---- LU of a resident view: mv x nv at V (leading dimension LD), view row 0 = global row/step row_off -----------
 // X (xcols columns, leading dimension FLD, rows aligned with the view's) receives the interchanges only: the L21
 // block of the left part while the trailing block is factored.
 // Warp 0 runs the pivot chains; warps 1..7 apply each finished sub-panel to the view: net row permutation on every
 // column, block row solve, rank-8 DMMA update -- the next sub-panel's eight columns FIRST, so that the chain warp
 // starts on them while the bulk of the update is still running (look-ahead of one sub-panel).
+#ifndef MB200_CHAIN
+#define MB200_CHAIN panel_chain_rolled  // panel_chain: the fully unrolled variant (A/B builds: -DMB200_CHAIN=panel_chain)
+#endif
 template <int LD, bool TRACK_PERM, int NU, typename SM>
 __device__ __forceinline__ void factor_view(SM &S, double *__restrict__ V, const int mv, const int nv, const int row_off,
                                             double *__restrict__ X, const int xcols, const int tid, const int lane, const int w)
@@ -322,10 +475,10 @@ __device__ __forceinline__ void factor_view(SM &S, double *__restrict__ V, const
             if (j > 0) f_bar_sync(BAR_NEXT, NT);
             const int k0 = j >> 5;
             const int na = ((mv + 31) >> 5) - k0;
-            if (LD > 98 && na >= 4) panel_chain<(LD > 98 ? 4 : 1), LD>(S, vbase, j, jb, mv, k0, lane, row_off);
-            else if (LD > 66 && na == 3) panel_chain<(LD > 66 ? 3 : 1), LD>(S, vbase, j, jb, mv, k0, lane, row_off);
-            else if (LD > 34 && na == 2) panel_chain<(LD > 34 ? 2 : 1), LD>(S, vbase, j, jb, mv, k0, lane, row_off);
-            else panel_chain<1, LD>(S, vbase, j, jb, mv, k0, lane, row_off);
+            if (LD > 98 && na >= 4) MB200_CHAIN<(LD > 98 ? 4 : 1), LD>(S, vbase, j, jb, mv, k0, lane, row_off);
+            else if (LD > 66 && na == 3) MB200_CHAIN<(LD > 66 ? 3 : 1), LD>(S, vbase, j, jb, mv, k0, lane, row_off);
+            else if (LD > 34 && na == 2) MB200_CHAIN<(LD > 34 ? 2 : 1), LD>(S, vbase, j, jb, mv, k0, lane, row_off);
+            else MB200_CHAIN<1, LD>(S, vbase, j, jb, mv, k0, lane, row_off);
             __threadfence_block();
             f_bar_arrive(BAR_PANEL, NT);
         }
@@ -381,7 +534,7 @@ __device__ __forceinline__ void factor_view(SM &S, double *__restrict__ V, const
                 for (int k = 0; k < 7; ++k) {
 #pragma unroll
                     for (int i = k + 1; i < 8; ++i)
-                        if (i < jb) x[i] = fma(-S.L11[i * 8 + k], x[k], x[i]);
+                        if (i < jb) x[i] = fma(-V[(j + k) * LD + j + i], x[k], x[i]);  // L11 from the permuted image
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -762,11 +915,19 @@ long rcp_selftest_run(long n, cudaStream_t s)
 magma_int_t panel_chain_launch(const Dims &d, double **dA, int **dipiv, int *dinfo, int j, int T, long batch, const int *il,
                                cudaStream_t s, unsigned short *sinv, int sinv_rows, int sinv_blocks)
 {
-    if (T <= 96 || T > 128 || batch <= 0) return -100;  // shorter panels: panel_kernel's higher occupancy wins (lu_blocked.cu)
-    static DevOnce once;
-    smem_optin(once, panel_chain_kernel<130, 6>, sizeof(PanelSmem<130>));
-    panel_chain_kernel<130, 6><<<(unsigned)batch, 64, sizeof(PanelSmem<130>), s>>>(d, dA, dipiv, dinfo, j, batch, il, sinv, sinv_rows,
-                                                                                 sinv_blocks);
+    if (T > 128 || batch <= 0) return -100;
+#define MB200_PC(LDV, MINB)                                                                                                   \
+    do {                                                                                                                      \
+        static DevOnce once;                                                                                                  \
+        smem_optin(once, panel_chain_kernel<LDV, MINB>, sizeof(PanelSmem<LDV>));                                              \
+        panel_chain_kernel<LDV, MINB><<<(unsigned)batch, 64, sizeof(PanelSmem<LDV>), s>>>(d, dA, dipiv, dinfo, j, batch, il, \
+                                                                                        sinv, sinv_rows, sinv_blocks);     \
+    } while (0)
+    if (T > 96) MB200_PC(130, 6);
+    else if (T > 64) MB200_PC(98, 8);
+    else if (T > 32) MB200_PC(66, 12);
+    else MB200_PC(34, 16);
+#undef MB200_PC
     count_launch();
     MB200_CHECK_LAUNCH("panel_chain_kernel");
     return 0;

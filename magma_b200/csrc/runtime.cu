@@ -10,7 +10,7 @@
 namespace mb200 {
 std::atomic<int64_t> g_launches{0};
 int g_tier = 0;
-int g_chain_panel = 1;
+int g_chain_panel = 3;
 static std::atomic<int> g_init_count{0};
 
 #ifdef MB200_INTERPOSE

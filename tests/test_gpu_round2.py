@@ -80,16 +80,18 @@ def test_fused_tier_full_size_sample(gpu_queue, fused_tier):
     check_against_oracle(gpu_queue, A0, n)
 
 
-@pytest.mark.parametrize("chain", [0, 1])
-@pytest.mark.parametrize("m,n,batch", [(128, 128, 7), (100, 100, 5), (97, 97, 5), (128, 40, 5), (120, 200, 4), (127, 96, 4), (226, 130, 3)])
+@pytest.mark.parametrize("chain", [0, 1, 3, 4])
+@pytest.mark.parametrize("m,n,batch", [(128, 128, 7), (100, 100, 5), (97, 97, 5), (128, 40, 5), (120, 200, 4), (127, 96, 4), (226, 130, 3),
+                                       (64, 64, 6), (65, 90, 4), (50, 45, 5), (33, 60, 4)])
 def test_chain_panel_switch(gpu_queue, chain, m, n, batch):
-    """Panels of 97..128 rows: single-warp chain kernel (default) and the one-thread-per-row kernel give the same bits."""
+    """Panels of at most 128 rows: the single-warp chain kernel (default: 33..128 rows) and the one-thread-per-row kernel
+    give the same bits at every switch level."""
     mb.set_chain_panel(chain)
     try:
         A0, _ = oracle.random_batch(batch, m, n)
         check_against_oracle(gpu_queue, A0, m)
     finally:
-        mb.set_chain_panel(1)
+        mb.set_chain_panel(3)
 
 
 def test_chain_panel_structured(gpu_queue):

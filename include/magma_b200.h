@@ -397,6 +397,8 @@ int64_t magma_b200_rcp_selftest(int64_t n, magma_queue_t queue);
 /* Level L = 1..4: 32-column panels of (128 - 32 L, 128] rows run on single-warp pivot chains (panel_chain_kernel);
  * default 3 (33..128 rows). 0: the one-thread-per-row panel kernel everywhere (A/B runs). */
 void magma_b200_set_chain_panel(int level);
+/* 1 (default): magma_dgetri_outofplace_batched runs its single-launch kernel for n <= 64; 0: identity + getrs for every n. */
+void magma_b200_set_getri_fused(int on);
 /* Largest max(m,n) routed to the single-launch shared-memory tier (lu_fused.cu), 0..128; 0 disables it (A/B runs). */
 void magma_b200_set_fused_max(int n);
 /* Largest max(m,n) routed to the register-file tier (lu_mid.cu), 32..128; for tuning sweeps. */

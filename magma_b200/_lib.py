@@ -95,6 +95,7 @@ SIGNATURES = {
     "magma_b200_set_mid_max": (None, [i32]),
     "magma_b200_set_fused_max": (None, [i32]),
     "magma_b200_set_chain_panel": (None, [i32]),
+    "magma_b200_set_getri_fused": (None, [i32]),
     "magma_b200_get_dgetrf_batched_crossover": (i32, [i32]),
     "magma_b200_rcp_selftest": (i64, [i64, vp]),
     "magma_dgemm_batched": (None, [i32, i32, i32, i32, i32, dbl, vp, i32, vp, i32, dbl, vp, i32, i32, vp]),

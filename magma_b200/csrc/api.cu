@@ -304,6 +304,7 @@ magma_int_t magma_dgesv_nopiv_batched(magma_int_t n, magma_int_t nrhs, double **
 // The reference forms U^-1 L^-1 I and then applies the column interchanges in reverse; column j of that product is
 // U^-1 L^-1 e_pi(j), i.e. exactly the solve A X = I with the interchanges applied to the identity first: one
 // identity fill + the getrs path (same kernels, same canonical order as oracle_dgetrs), nothing is re-derived.
+// n <= 64 runs the same arithmetic in one launch (getri.cu: permuted identity built in registers, DMMA block updates).
 // Like the reference, info_array is not written and dA_array is left untouched.
 magma_int_t magma_dgetri_outofplace_batched(magma_int_t n, double **dA_array, magma_int_t ldda,
                                             magma_int_t **dipiv_array, double **dinvA_array, magma_int_t lddia,
@@ -319,6 +320,8 @@ magma_int_t magma_dgetri_outofplace_batched(magma_int_t n, double **dA_array, ma
         return info;
     }
     if (n == 0 || batchCount <= 0) return 0;
+    const magma_int_t rc = getri_fused_launch(n, dA_array, ldda, dipiv_array, dinvA_array, lddia, batchCount, MB200_Q(queue)->stream);
+    if (rc != -100) return rc;
     identity_launch(n, dinvA_array, lddia, batchCount, MB200_Q(queue)->stream);
     return magma_dgetrs_batched(MagmaNoTrans, n, n, dA_array, ldda, dipiv_array, dinvA_array, lddia, batchCount, queue);
 }

@@ -197,6 +197,9 @@ void displace_pointers_launch(void **out, void **in, long elem, long lda, long r
                               long batch, cudaStream_t s);
 void memset_int_launch(int *p, int v, long n, cudaStream_t s);
 void identity_launch(int n, double **dB, int lddb, long batch, cudaStream_t s);
+// getri.cu: single-launch out-of-place inverse from the factors, n <= 64; -100 = not covered
+magma_int_t getri_fused_launch(int n, double **dA, int ldda, int **dipiv, double **dinvA, int lddia, long batch,
+                               cudaStream_t s);
 // vbatched statistics: out[0..15] = {max_m, max_n, max_minmn, max_mxn(clamped), first_bad_arg,
 // count(max(m,n) <= 32), count_nonempty, 0, count(<= 64), count(<= 96), count(<= 128), ...}
 void vbatched_stats_launch(const int *m, const int *n, const int *ldda, long batch, int *out16,

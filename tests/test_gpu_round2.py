@@ -696,3 +696,61 @@ def test_c_program_links_and_runs(tmp_path, lib):
     ipr, infr = oracle.getrf_batched(ref, n)
     assert np.array_equal(ipiv, ipr)
     assert np.array_equal(LU, ref)
+
+
+# ---- single-launch inverse (getri.cu) ---------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n,ldda,lddia", [(1, 1, 1), (2, 2, 2), (5, 5, 8), (8, 8, 8), (9, 12, 9), (16, 16, 16), (24, 25, 24), (31, 31, 33),
+                                          (32, 32, 32), (33, 34, 33), (40, 40, 44), (47, 48, 47), (48, 48, 48), (56, 56, 56),
+                                          (63, 63, 64), (64, 64, 64), (64, 70, 66)])
+def test_getri_fused(gpu_queue, n, ldda, lddia):
+    """magma_dgetri_outofplace_batched for n <= 64 (one launch, DMMA block updates): bit-identical to the oracle and to the
+    identity + getrs path it replaces; padding of A and of inv(A) untouched."""
+    import torch
+    batch = 11
+    A0, _ = oracle.random_batch(batch, n, n)
+    db = mb.DeviceBatch(batch, n, n, ldda=ldda, queue=gpu_queue)
+    Ain = np.full((batch, n, ldda), 3.5)
+    Ain[:, :, :n] = A0
+    db.upload(Ain)
+    assert db.getrf() == 0
+    LU, ipiv, info = db.download()
+    assert not info.any()
+    out = {}
+    for mode in (1, 0):
+        mb.set_getri_fused(mode)
+        try:
+            X = torch.full((batch, n, lddia), -2.25, dtype=torch.float64, device="cuda")
+            base = X.data_ptr()
+            ptrs = torch.tensor([base + b * n * lddia * 8 for b in range(batch)], dtype=torch.int64, device="cuda")
+            assert mb.magma_dgetri_outofplace_batched(n, db.dA_array, db.ldda, db.dipiv_array, ptrs, lddia, db.info, batch,
+                                                      gpu_queue) == 0
+            gpu_queue.sync()
+            out[mode] = X.cpu().numpy()
+        finally:
+            mb.set_getri_fused(1)
+    Xr = oracle.getri_outofplace_batched(np.ascontiguousarray(LU[:, :, :n]), ipiv, n)
+    assert np.array_equal(out[1][:, :, :n], Xr), f"max diff {np.max(np.abs(out[1][:, :, :n] - Xr))}"
+    assert np.array_equal(out[0], out[1])
+    assert np.all(out[1][:, :, n:] == -2.25)
+    LU2, _, _ = db.download()
+    assert np.array_equal(LU2, LU)  # the factors are read only
+
+
+def test_getri_fused_identity_and_permutation(gpu_queue):
+    """Structured factors: identity, a pure permutation, unit-diagonal triangular."""
+    n = 64
+    rng = np.random.default_rng(5)
+    P = np.eye(n)[rng.permutation(n)]
+    Lo = np.tril(rng.random((n, n)), -1) * 0.01 + np.eye(n)
+    mats = np.stack([np.eye(n), P, Lo, Lo.T, 3.0 * np.eye(n)])
+    batch = len(mats)
+    db = mb.DeviceBatch(batch, n, n, nrhs=n, queue=gpu_queue)
+    db.upload(mats, np.zeros((batch, n, n)))
+    assert db.getrf() == 0
+    assert mb.magma_dgetri_outofplace_batched(n, db.dA_array, db.ldda, db.dipiv_array, db.dB_array, db.lddb, db.info, batch,
+                                              gpu_queue) == 0
+    LU, ipiv, info, X = db.download()
+    Xr = oracle.getri_outofplace_batched(LU, ipiv, n)
+    assert np.array_equal(X, Xr)
+    assert np.array_equal(X[0], np.eye(n)) and np.array_equal(X[1].T @ P.T, np.eye(n))

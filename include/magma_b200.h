@@ -238,6 +238,50 @@ magma_int_t magma_dgetrf_vbatched(magma_int_t *m, magma_int_t *n, double **dA_ar
                                   magma_int_t **ipiv_array, magma_int_t *info_array,
                                   magma_int_t batchCount, magma_queue_t queue);
 
+/* ---- s / c / z precisions of the four entry points -------------------------------------------------
+ * The reference generates them from the z masters (src/zgetrf_batched.cpp:11 "@precisions normal z -> s d c");
+ * signatures: include/magma_zbatched.h:848 (getrf), :464 (getrs), :1009 (gesv), include/magma_zvbatched.h:57 (getrf_vbatched)
+ * and their generated s / c counterparts. One templated implementation (csrc/lu_scz.cu), bit-identical to
+ * oracle/lu_oracle_scz.c; complex pivoting uses |re| + |im| like the reference's device code. */
+typedef struct { float x, y; } magmaFloatComplex;   /* layout of cuFloatComplex (include/magma_types.h:100) */
+typedef struct { double x, y; } magmaDoubleComplex; /* layout of cuDoubleComplex */
+magma_int_t magma_sgetrf_batched(magma_int_t m, magma_int_t n, float **dA_array, magma_int_t ldda,
+                                 magma_int_t **ipiv_array, magma_int_t *info_array, magma_int_t batchCount,
+                                 magma_queue_t queue);
+magma_int_t magma_sgetrs_batched(magma_trans_t trans, magma_int_t n, magma_int_t nrhs, float **dA_array,
+                                 magma_int_t ldda, magma_int_t **dipiv_array, float **dB_array, magma_int_t lddb,
+                                 magma_int_t batchCount, magma_queue_t queue);
+magma_int_t magma_sgesv_batched(magma_int_t n, magma_int_t nrhs, float **dA_array, magma_int_t ldda,
+                                magma_int_t **dipiv_array, float **dB_array, magma_int_t lddb,
+                                magma_int_t *dinfo_array, magma_int_t batchCount, magma_queue_t queue);
+magma_int_t magma_sgetrf_vbatched(magma_int_t *m, magma_int_t *n, float **dA_array, magma_int_t *ldda,
+                                  magma_int_t **ipiv_array, magma_int_t *info_array, magma_int_t batchCount,
+                                  magma_queue_t queue);
+magma_int_t magma_cgetrf_batched(magma_int_t m, magma_int_t n, magmaFloatComplex **dA_array, magma_int_t ldda,
+                                 magma_int_t **ipiv_array, magma_int_t *info_array, magma_int_t batchCount,
+                                 magma_queue_t queue);
+magma_int_t magma_cgetrs_batched(magma_trans_t trans, magma_int_t n, magma_int_t nrhs, magmaFloatComplex **dA_array,
+                                 magma_int_t ldda, magma_int_t **dipiv_array, magmaFloatComplex **dB_array, magma_int_t lddb,
+                                 magma_int_t batchCount, magma_queue_t queue);
+magma_int_t magma_cgesv_batched(magma_int_t n, magma_int_t nrhs, magmaFloatComplex **dA_array, magma_int_t ldda,
+                                magma_int_t **dipiv_array, magmaFloatComplex **dB_array, magma_int_t lddb,
+                                magma_int_t *dinfo_array, magma_int_t batchCount, magma_queue_t queue);
+magma_int_t magma_cgetrf_vbatched(magma_int_t *m, magma_int_t *n, magmaFloatComplex **dA_array, magma_int_t *ldda,
+                                  magma_int_t **ipiv_array, magma_int_t *info_array, magma_int_t batchCount,
+                                  magma_queue_t queue);
+magma_int_t magma_zgetrf_batched(magma_int_t m, magma_int_t n, magmaDoubleComplex **dA_array, magma_int_t ldda,
+                                 magma_int_t **ipiv_array, magma_int_t *info_array, magma_int_t batchCount,
+                                 magma_queue_t queue);
+magma_int_t magma_zgetrs_batched(magma_trans_t trans, magma_int_t n, magma_int_t nrhs, magmaDoubleComplex **dA_array,
+                                 magma_int_t ldda, magma_int_t **dipiv_array, magmaDoubleComplex **dB_array, magma_int_t lddb,
+                                 magma_int_t batchCount, magma_queue_t queue);
+magma_int_t magma_zgesv_batched(magma_int_t n, magma_int_t nrhs, magmaDoubleComplex **dA_array, magma_int_t ldda,
+                                magma_int_t **dipiv_array, magmaDoubleComplex **dB_array, magma_int_t lddb,
+                                magma_int_t *dinfo_array, magma_int_t batchCount, magma_queue_t queue);
+magma_int_t magma_zgetrf_vbatched(magma_int_t *m, magma_int_t *n, magmaDoubleComplex **dA_array, magma_int_t *ldda,
+                                  magma_int_t **ipiv_array, magma_int_t *info_array, magma_int_t batchCount,
+                                  magma_queue_t queue);
+
 /* Expert forms.   src/zgetrf_vbatched.cpp:223-336 and :19-130
  * _work: lwork[0] < 0 is a workspace query (required bytes returned in lwork[0]); asynchronous. */
 magma_int_t magma_dgetrf_vbatched_max_nocheck_work(

@@ -96,6 +96,18 @@ SIGNATURES = {
     "magma_b200_set_fused_max": (None, [i32]),
     "magma_b200_set_chain_panel": (None, [i32]),
     "magma_b200_set_getri_fused": (None, [i32]),
+    "magma_sgetrf_batched": (i32, [i32, i32, vp, i32, vp, vp, i32, vp]),
+    "magma_sgetrs_batched": (i32, [i32, i32, i32, vp, i32, vp, vp, i32, i32, vp]),
+    "magma_sgesv_batched": (i32, [i32, i32, vp, i32, vp, vp, i32, vp, i32, vp]),
+    "magma_sgetrf_vbatched": (i32, [vp, vp, vp, vp, vp, vp, i32, vp]),
+    "magma_cgetrf_batched": (i32, [i32, i32, vp, i32, vp, vp, i32, vp]),
+    "magma_cgetrs_batched": (i32, [i32, i32, i32, vp, i32, vp, vp, i32, i32, vp]),
+    "magma_cgesv_batched": (i32, [i32, i32, vp, i32, vp, vp, i32, vp, i32, vp]),
+    "magma_cgetrf_vbatched": (i32, [vp, vp, vp, vp, vp, vp, i32, vp]),
+    "magma_zgetrf_batched": (i32, [i32, i32, vp, i32, vp, vp, i32, vp]),
+    "magma_zgetrs_batched": (i32, [i32, i32, i32, vp, i32, vp, vp, i32, i32, vp]),
+    "magma_zgesv_batched": (i32, [i32, i32, vp, i32, vp, vp, i32, vp, i32, vp]),
+    "magma_zgetrf_vbatched": (i32, [vp, vp, vp, vp, vp, vp, i32, vp]),
     "magma_b200_get_dgetrf_batched_crossover": (i32, [i32]),
     "magma_b200_rcp_selftest": (i64, [i64, vp]),
     "magma_dgemm_batched": (None, [i32, i32, i32, i32, i32, dbl, vp, i32, vp, i32, dbl, vp, i32, i32, vp]),

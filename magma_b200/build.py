@@ -20,7 +20,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmagma_b200.so")
 LIB_INTERPOSE = os.path.join(LIBDIR, "libmagma_b200_interpose.so")
 
-SOURCES = ["runtime.cu", "aux.cu", "lu_small.cu", "lu_small_sq.cu", "lu_mid.cu", "lu_fused.cu", "lu_blocked.cu", "getrs.cu", "getri.cu", "compat.cu", "rbt.cu", "blas3.cu", "api.cu"]
+SOURCES = ["runtime.cu", "aux.cu", "lu_small.cu", "lu_small_sq.cu", "lu_mid.cu", "lu_fused.cu", "lu_blocked.cu", "getrs.cu", "getri.cu", "lu_scz.cu", "compat.cu", "rbt.cu", "blas3.cu", "api.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",

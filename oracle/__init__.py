@@ -20,11 +20,12 @@ _BUILD = os.path.join(_HERE, "_build")
 MagmaNoTrans, MagmaTrans, MagmaConjTrans = 111, 112, 113
 
 
-def _compile(src: str, out: str, extra=()):
+def _compile(src: str, out: str, extra=(), deps=()):
     os.makedirs(_BUILD, exist_ok=True)
     srcp = os.path.join(_HERE, src)
     outp = os.path.join(_BUILD, out)
-    if os.path.exists(outp) and os.path.getmtime(outp) >= os.path.getmtime(srcp):
+    newest = max(os.path.getmtime(os.path.join(_HERE, f)) for f in (src, *deps))
+    if os.path.exists(outp) and os.path.getmtime(outp) >= newest:
         return outp
     cmd = ["gcc", "-O3", "-mavx2", "-mfma", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC",
            "-o", outp + ".tmp", srcp, "-lm", *extra]
@@ -36,7 +37,8 @@ def _compile(src: str, out: str, extra=()):
 def build():
     """Compile both checker libraries (idempotent). Returns their paths."""
     return (_compile("lu_oracle.c", "liblu_oracle.so"),
-            _compile("lapack_loop.c", "liblapack_loop.so", extra=("-ldl",)))
+            _compile("lapack_loop.c", "liblapack_loop.so", extra=("-ldl",)),
+            _compile("lu_oracle_scz.c", "liblu_oracle_scz.so", deps=("lu_oracle_tmpl.h",)))
 
 
 _lib = None
@@ -320,3 +322,70 @@ def gemm_lu_update(A: np.ndarray, B: np.ndarray, Cm: np.ndarray):
     k, m = A.shape
     n = B.shape[0]
     lib().oracle_dgemm_lu_update(m, n, k, A.reshape(-1), m, B.reshape(-1), B.shape[1], Cm.reshape(-1), Cm.shape[1])
+
+
+# ---- s / c / z: lu_oracle_scz.c ---------------------------------------------------------------
+# p is one of "s", "c", "z" ("q" = the same template in double, used only to pin the template against lu_oracle.c).
+PREC_DTYPE = {"s": np.float32, "c": np.complex64, "z": np.complex128, "q": np.float64}
+_scz = None
+
+
+def lib_scz():
+    global _scz
+    if _scz is None:
+        L = C.CDLL(build()[2])
+        vp = C.c_void_p
+        for p in PREC_DTYPE:
+            getattr(L, f"oracle_{p}getrf_batched").argtypes = [_i, _i, vp, _i, _l, _pi, _l, _pi, _l]
+            getattr(L, f"oracle_{p}getrs_batched").argtypes = [_i, _i, _i, vp, _i, _l, _pi, _l, vp, _i, _l, _l]
+            getattr(L, f"oracle_{p}gesv_batched").argtypes = [_i, _i, vp, _i, _l, _pi, _l, vp, _i, _l, _pi, _l]
+        _scz = L
+    return _scz
+
+
+def _chk(p, *arrs):
+    for a in arrs:
+        assert a.dtype == PREC_DTYPE[p] and a.flags.c_contiguous, (a.dtype, p)
+
+
+def random_batch_prec(p: str, batch: int, m: int, n: int, ld: int | None = None, seed: int = 0) -> np.ndarray:
+    """batch matrices m x n, uniform in (0,1) (both parts for c / z), stored (batch, n, ld) column-major like random_batch."""
+    ld = m if ld is None else ld
+    rng = np.random.default_rng(seed)
+    A = np.zeros((batch, n, ld), dtype=PREC_DTYPE[p])
+    x = rng.random((batch, n, m))
+    if p in ("c", "z"):
+        x = x + 1j * rng.random((batch, n, m))
+    A[:, :, :m] = x.astype(PREC_DTYPE[p])
+    return A
+
+
+def getrf_batched_prec(p: str, A: np.ndarray, m: int):
+    """In-place LU of A[batch, n, ld] in precision p; returns (ipiv, info) like getrf_batched."""
+    _chk(p, A)
+    batch, n, ld = A.shape
+    mn = min(m, n)
+    ipiv = np.zeros((batch, max(mn, 1)), dtype=np.int32)
+    info = np.zeros(batch, dtype=np.int32)
+    getattr(lib_scz(), f"oracle_{p}getrf_batched")(m, n, A.ctypes.data, ld, n * ld, ipiv.reshape(-1), max(mn, 1), info, batch)
+    return ipiv[:, :mn], info
+
+
+def getrs_batched_prec(p: str, trans: int, LU: np.ndarray, ipiv: np.ndarray, B: np.ndarray, n: int):
+    _chk(p, LU, B)
+    batch, _, lda = LU.shape
+    _, nrhs, ldb = B.shape
+    ip = np.ascontiguousarray(ipiv, dtype=np.int32)
+    getattr(lib_scz(), f"oracle_{p}getrs_batched")(trans, n, nrhs, LU.ctypes.data, lda, LU.shape[1] * lda, ip.reshape(-1),
+                                                   ip.shape[1], B.ctypes.data, ldb, nrhs * ldb, batch)
+
+
+def gesv_batched_prec(p: str, A: np.ndarray, B: np.ndarray, n: int):
+    _chk(p, A, B)
+    batch, _, lda = A.shape
+    _, nrhs, ldb = B.shape
+    ipiv = np.zeros((batch, n), dtype=np.int32)
+    info = np.zeros(batch, dtype=np.int32)
+    getattr(lib_scz(), f"oracle_{p}gesv_batched")(n, nrhs, A.ctypes.data, lda, A.shape[1] * lda, ipiv.reshape(-1), n,
+                                                  B.ctypes.data, ldb, nrhs * ldb, info, batch)
+    return ipiv, info

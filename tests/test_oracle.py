@@ -233,3 +233,66 @@ def test_rbt_restatement_is_consistent():
     info = oracle.gesv_rbt_batched(A, B, n, u, v)
     assert not info.any()
     assert oracle.solve_residual(oracle.MagmaNoTrans, A0, B, B0, n) < 1e-9  # no pivoting: looser than the 30 eps bar
+
+
+def test_scz_template_equals_double_oracle():
+    """lu_oracle_tmpl.h instantiated in double ("q") reproduces oracle_dgetf2 / oracle_dgetrs / oracle_dgesv bit for bit:
+    the s / c / z restatements are the same algorithm, not a second one."""
+    A0, _ = oracle.random_batch(7, 45, 38)
+    a, b = A0.copy(), A0.copy()
+    ip1, in1 = oracle.getrf_batched(a, 45)
+    ip2, in2 = oracle.getrf_batched_prec("q", b, 45)
+    assert np.array_equal(a, b) and np.array_equal(ip1, ip2) and np.array_equal(in1, in2)
+    A0, _ = oracle.random_batch(5, 30, 30)
+    B0, _ = oracle.random_batch(5, 30, 4)
+    LU = A0.copy()
+    ip, _ = oracle.getrf_batched(LU, 30)
+    for tr in (111, 112, 113):
+        x1, x2 = B0.copy(), B0.copy()
+        oracle.getrs_batched(tr, LU, ip, x1, 30)
+        oracle.getrs_batched_prec("q", tr, LU, ip, x2, 30)
+        assert np.array_equal(x1, x2)
+    a1, b1, a2, b2 = A0.copy(), B0.copy(), A0.copy(), B0.copy()
+    oracle.gesv_batched(a1, b1, 30)
+    oracle.gesv_batched_prec("q", a2, b2, 30)
+    assert np.array_equal(a1, a2) and np.array_equal(b1, b2)
+
+
+@pytest.mark.parametrize("p", ["s", "c", "z"])
+def test_scz_oracle_vs_lapack(p):
+    """oracle_{s,c,z}getf2 / getrs against LAPACK (scipy): identical pivots, factors and solutions to a small multiple of
+    n * eps of the precision (the reference testers' criterion, testing/testing_zgetrf_batched.cpp:41-81)."""
+    import scipy.linalg as sl
+    eps = float(np.finfo(oracle.PREC_DTYPE[p]).eps)
+    for n in (8, 32, 64, 150):
+        A = oracle.random_batch_prec(p, 3, n, n, seed=n)
+        LU = A.copy()
+        ip, info = oracle.getrf_batched_prec(p, LU, n)
+        assert not info.any()
+        for b in range(3):
+            lu, piv = sl.lu_factor(A[b].T)
+            assert np.array_equal(piv + 1, ip[b])
+            assert np.abs(lu - LU[b].T).max() <= 4 * n * eps * np.abs(lu).max()
+        B = oracle.random_batch_prec(p, 3, n, 2, seed=n + 1)
+        for tr in (111, 112, 113):
+            X = B.copy()
+            oracle.getrs_batched_prec(p, tr, LU, ip, X, n)
+            for b in range(3):
+                M = A[b].T
+                op = {111: M, 112: M.T, 113: M.conj().T}[tr]
+                r = np.linalg.norm(op @ X[b].T - B[b].T, 1) / (n * np.linalg.norm(M, 1) * np.linalg.norm(X[b].T, 1))
+                assert r < 30 * eps
+    # rectangular: P A = L U
+    for (m, n) in ((40, 25), (25, 40)):
+        A = oracle.random_batch_prec(p, 2, m, n, seed=m)
+        LU = A.copy()
+        ip, _ = oracle.getrf_batched_prec(p, LU, m)
+        k = min(m, n)
+        for b in range(2):
+            M = A[b].T.copy()
+            for i in range(k):
+                pi = ip[b, i] - 1
+                M[[i, pi]] = M[[pi, i]]
+            Lm = np.tril(LU[b].T[:, :k], -1) + np.eye(m, k)
+            Um = np.triu(LU[b].T[:k, :])
+            assert np.abs(M - Lm @ Um).max() <= 4 * k * eps * np.abs(M).max()

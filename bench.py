@@ -521,7 +521,7 @@ def run_sweep(mb, torch, np, q, local, rank, world, barrier, max_over_ranks, sum
     fixed("C5 dgetrf_batched n=512 batch=4000 (+dgetrs nrhs=16)", 512, 4_000, nrhs=16, solve_after=True, reps=3)
     fixed("X1 dgetrf_batched n=256 batch=16000 (left-looking slab driver)", 256, 16_000, reps=3)
 
-    # F1: out-of-place inverse from the factors, n = 64: identity fill + the getrs path.
+    # F1: out-of-place inverse from the factors, n = 64: one launch for n <= 64 (csrc/getri.cu); identity fill + the getrs path above that.
     # FLOPs: testing/flops.h:87-88,279 (FLOPS_DGETRI); bytes: read LU, write inv(A).
     def getri(name, n, batch, reps=5):
         db = mb.DeviceBatch(batch, n, n, nrhs=n, device=local, queue=q)
@@ -563,6 +563,40 @@ def run_sweep(mb, torch, np, q, local, rank, world, barrier, max_over_ranks, sum
         torch.cuda.empty_cache()
 
     nopiv("F2 dgetrf_nopiv_batched n=128 batch=50000", 128, 50_000)
+
+    # P1-P3: the s / c / z entry points (csrc/lu_scz.cu: coverage kernels, not tuned to the roofline).
+    # bytes: read + write the matrix in its own element size; flops: real = FLOPS_DGETRF, complex = 4x (testing/flops.h:24-27)
+    def prec(name, p, n, batch, reps=5):
+        from magma_b200 import _lib
+        dev = torch.device("cuda", local)
+        rdt, dt = {"s": (torch.float32, torch.float32), "c": (torch.float32, torch.complex64),
+                   "z": (torch.float64, torch.complex128)}[p]
+        g = torch.Generator(device=dev)
+        g.manual_seed(51 + rank)
+        A = torch.rand((batch, n, n), dtype=rdt, device=dev, generator=g)
+        if p != "s":
+            A = torch.complex(A, torch.rand((batch, n, n), dtype=rdt, device=dev, generator=g))
+        A0 = A.clone()
+        esz = A.element_size()
+        idx = torch.arange(batch, dtype=torch.int64, device=dev)
+        ip = torch.zeros((batch, n), dtype=torch.int32, device=dev)
+        info = torch.zeros(batch, dtype=torch.int32, device=dev)
+        pA, pP = idx * (n * n * esz) + A.data_ptr(), idx * (n * 4) + ip.data_ptr()
+        f = getattr(_lib.load(), f"magma_{p}getrf_batched")
+        fn = lambda: f(n, n, pA.data_ptr(), n, pP.data_ptr(), info.data_ptr(), batch, q.handle)  # noqa: E731
+        med, best = timed(fn, lambda: A.copy_(A0), reps)
+        fl = flops_getrf(n, n) * (1.0 if p == "s" else 4.0)
+        out.append({"config": name, "n": n, "batch_per_gpu": batch, "ms": med, "ms_best": best,
+                    "gflops": fl * batch * world / (med * 1e-3) / 1e9, "dtype": {"s": "f32", "c": "c64", "z": "c128"}[p],
+                    "alg_GBs_per_gpu": 2.0 * esz * n * n * batch / (med * 1e-3) / 1e9,
+                    "frac_of_hbm": 2.0 * esz * n * n * batch / (med * 1e-3) / 1e9 / hbm_peak,
+                    "info_max": int(info.abs().max().item())})
+        del A, A0, ip, info
+        torch.cuda.empty_cache()
+
+    prec("P1 sgetrf_batched n=32 batch=1000000", "s", 32, 1_000_000)
+    prec("P2 zgetrf_batched n=32 batch=250000", "z", 32, 250_000)
+    prec("P3 cgetrf_batched n=64 batch=50000", "c", 64, 50_000, reps=3)
 
     # C4: vbatched, sizes 16 + (lcg mod 497), square, ldda = n
     batch = 20_000

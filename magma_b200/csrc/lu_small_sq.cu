@@ -325,6 +325,15 @@ __device__ __forceinline__ double sel64(unsigned flag, double x1, double x0)
     return d;
 }
 
+template <int I, int N, typename F>
+__device__ __forceinline__ void sq_static_for(F &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        sq_static_for<I + 1, N>(f);
+    }
+}
+
 template <int N>
 struct SqsSmem {           // one per matrix in flight (fused-solve variant only)
     double stage[N * N];   // factors in final row order, dense column-major
@@ -374,7 +383,7 @@ lu_sqs_kernel(double *const *__restrict__ dA, int *const *__restrict__ dipiv, in
     // warp load touched four half-used lines: 4 tag wavefronts per 8-byte instruction, 136 per pass instead of 68).
     // Which rows a lane starts with is immaterial afterwards: everything below works on positions.
     // (n = 8 keeps rows sub and sub + G: the 64-register budget of that variant does not survive the extra path.)
-    constexpr bool ADJ = (N == 16);
+    constexpr bool ADJ = (N >= 16);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         pos[r] = (unsigned)(ADJ ? 2 * sub + r : sub + r * G);
@@ -402,8 +411,10 @@ lu_sqs_kernel(double *const *__restrict__ dA, int *const *__restrict__ dipiv, in
     }
     unsigned zmask = 0;  // bit i set: column i had an exactly zero pivot
 
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
+    // both loops expanded at compile time: a `#pragma unroll` nest of the n = 32 size is left rolled by nvcc, with a[][]
+    // in local memory
+    sq_static_for<0, N>([&](auto ic_) {
+        constexpr int i = decltype(ic_)::value;
         if (LOCK) __syncthreads();
         // ---- pivot search: high words first ------------------------------------------------------
         bool act[R];
@@ -459,18 +470,18 @@ lu_sqs_kernel(double *const *__restrict__ dA, int *const *__restrict__ dipiv, in
             l[r] = upd ? a[r][i] * rr : 0.0;
             if (upd) a[r][i] = l[r];
         }
-#pragma unroll
-        for (int j = i + 1; j < N; ++j) {
+        sq_static_for<i + 1, N>([&](auto jc_) {
+            constexpr int j = decltype(jc_)::value;
             const double u = shfl64(sel64(take1, a[1][j], a[0][j]), P);
 #pragma unroll
             for (int r = 0; r < R; ++r) a[r][j] = fma(-l[r], u, a[r][j]);
-        }
+        });
         if (NRHS) {
             const double ub = shfl64(sel64(take1, rb[1], rb[0]), P);
 #pragma unroll
             for (int r = 0; r < R; ++r) rb[r] = fma(-l[r], ub, rb[r]);
         }
-    }
+    });
 
     if (!NRHS) {
         // ---- factor only: straight from registers, 8-byte stores at the final row positions --------------
@@ -603,7 +614,10 @@ magma_int_t lu_sq_launch(int n, double **dA, int ldda, int **dipiv, int *dinfo, 
             case 16:
                 if (g_small_rows == 4) return launch_sqs<16, 8, 0, 4, 4, false>(dA, ldda, dipiv, dinfo, dB, batch, s);
                 return launch_sqs<16, 8, 0, 5, 4, false>(dA, ldda, dipiv, dinfo, dB, batch, s);
-            case 32: return g_small_rows == 3 ? launch_sq<32, 32, 1, 0, 4>(dA, ldda, dipiv, dinfo, dB, batch, s) : -100;
+            case 32:
+                if (g_small_rows == 5) return launch_sqs<32, 16, 0, 3, 4, false>(dA, ldda, dipiv, dinfo, dB, batch, s);
+                if (g_small_rows == 6) return launch_sqs<32, 16, 0, 2, 4, false>(dA, ldda, dipiv, dinfo, dB, batch, s);
+                return g_small_rows == 3 ? launch_sq<32, 32, 1, 0, 4>(dA, ldda, dipiv, dinfo, dB, batch, s) : -100;
             default: return -100;
         }
     }

@@ -448,7 +448,8 @@ void magma_b200_set_fused_max(int n);
 /* Largest max(m,n) routed to the register-file tier (lu_mid.cu), 32..128; for tuning sweeps. */
 void magma_b200_set_mid_max(int n);
 /* Register tier layout override for tuning sweeps: rows per lane (1 or 2), 0 = tuned default; 3/4 = alternative
- * square kernels (n = 32 staged / n = 16 with 4 CTAs per SM), 7 = keep the register-file tier on 65..96
+ * square kernels (n = 32 staged / n = 16 with 4 CTAs per SM), 5/6 = n = 32 on the shuffle-broadcast square kernel with 16
+ * lanes x 2 rows per matrix (3 / 2 CTAs per SM; 7.5 ms per 10^6 against 6.2 ms), 7 = keep the register-file tier on 65..96
  * (default: left-looking blocked driver there), 8 = single-phase 16-warp register-file kernel, 9 = generic kernel only. */
 void magma_b200_set_small_rows(int rows);
 

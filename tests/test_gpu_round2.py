@@ -754,3 +754,15 @@ def test_getri_fused_identity_and_permutation(gpu_queue):
     Xr = oracle.getri_outofplace_batched(LU, ipiv, n)
     assert np.array_equal(X, Xr)
     assert np.array_equal(X[0], np.eye(n)) and np.array_equal(X[1].T @ P.T, np.eye(n))
+
+
+@pytest.mark.parametrize("rows", [2, 3, 5, 6, 9])
+def test_register_tier_layout_switches_n32(gpu_queue, rows):
+    """The alternative n = 32 layouts behind magma_b200_set_small_rows (two rows per lane generic / staged square /
+    shuffle-broadcast square with 16 lanes per matrix / generic only): slower than the default, same bits."""
+    mb.set_small_rows(rows)
+    try:
+        A0, _ = oracle.random_batch(41, 32, 32)
+        check_against_oracle(gpu_queue, A0, 32)
+    finally:
+        mb.set_small_rows(0)

@@ -296,3 +296,29 @@ def test_scz_oracle_vs_lapack(p):
             Lm = np.tril(LU[b].T[:, :k], -1) + np.eye(m, k)
             Um = np.triu(LU[b].T[:k, :])
             assert np.abs(M - Lm @ Um).max() <= 4 * k * eps * np.abs(M).max()
+
+
+GOLD_SCZ = np.load(os.path.join(os.path.dirname(__file__), "golden", "lu_golden_scz.npz"))
+
+
+@pytest.mark.parametrize("key", sorted({k.rsplit("_", 1)[0] for k in GOLD_SCZ.files if k.endswith("_A")}))
+def test_scz_oracle_vs_golden(key):
+    """oracle_{s,c,z}getf2 / getrs against the committed LAPACK {s,c,z}getrf / getrs vectors (tests/golden/make_golden_scz.py):
+    pivots identical, factors and solutions within a few n * eps of the precision."""
+    p = key[0]
+    A = GOLD_SCZ[key + "_A"]
+    m, n = A.shape
+    eps = float(np.finfo(oracle.PREC_DTYPE[p]).eps)
+    LU = np.ascontiguousarray(A.T)[None].copy()  # stored layout (batch, n, ld = m)
+    ip, info = oracle.getrf_batched_prec(p, LU, m)
+    assert info[0] == 0
+    assert np.array_equal(ip[0], GOLD_SCZ[key + "_ipiv"])
+    want = GOLD_SCZ[key + "_LU"]
+    assert np.abs(LU[0].T - want).max() <= 4 * max(m, n) * eps * np.abs(want).max()
+    if m == n:
+        B = GOLD_SCZ[key + "_B"]
+        for tr, name in ((111, "N"), (112, "T"), (113, "C")):
+            X = np.ascontiguousarray(B.T)[None].copy()
+            oracle.getrs_batched_prec(p, tr, LU, ip, X, n)
+            wx = GOLD_SCZ[key + "_X" + name]
+            assert np.abs(X[0].T - wx).max() <= 40 * n * eps * np.abs(wx).max()

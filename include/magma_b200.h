@@ -441,6 +441,10 @@ int64_t magma_b200_rcp_selftest(int64_t n, magma_queue_t queue);
 /* Level L = 1..4: 32-column panels of (128 - 32 L, 128] rows run on single-warp pivot chains (panel_chain_kernel);
  * default 3 (33..128 rows). 0: the one-thread-per-row panel kernel everywhere (A/B runs). */
 void magma_b200_set_chain_panel(int level);
+/* Matrices of at most 128 rows in the left-looking driver: 1 = panels of 33..96 rows are factored in the tail of the slab
+ * kernel that updated them (no panel launch, no slab round trip), 2 = the last <= 32-row panel too, 0 = off (default:
+ * four chains per SM in the slab kernel lose to the 8..12 of the panel kernels, n = 128: 8.99 -> 9.69 ms). */
+void magma_b200_set_fused_tail(int level);
 /* 1 (default): magma_dgetri_outofplace_batched runs its single-launch kernel for n <= 64; 0: identity + getrs for every n. */
 void magma_b200_set_getri_fused(int on);
 /* Largest max(m,n) routed to the single-launch shared-memory tier (lu_fused.cu), 0..128; 0 disables it (A/B runs). */

@@ -30,8 +30,7 @@
 //   update_strip_kernel, laswp_left_kernel : short trailing strips in shared memory; deferred
 //                   interchanges replayed from ipiv.
 // All arithmetic is in the canonical order of oracle/lu_oracle.c: bit-identical factors.
-#include "lu_common.cuh"
-#include <type_traits>
+#include "lu_chain.cuh"
 
 namespace mb200 {
 
@@ -1122,11 +1121,24 @@ struct LeftSmem {
     alignas(16) double ring[RING * 8 * LDR];  // L chunks, CTA-wide, rows in the order of their own panel
 };
 
+// scratch of the fused tail (factor_view's bookkeeping), overlaid on Us once the update loop is over
+struct TailSmem {
+    static constexpr int LDU = 36;
+    double Un[8 * 36];
+    double L11[64];
+    int ipiv[128];
+    int nmoves, info;
+    unsigned char mdst[16], msrc[16], perm[128];
+};
+
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, NW == 16 ? 1 : (NW == 8 ? 2 : 4))
 left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__restrict__ sinv_g, int sinv_rows,
-                   int sinv_blocks, int J, int finish, int ahead, int use_bulk, long batch, const int *__restrict__ index_list)
+                   int sinv_blocks, int J, int finish, int ahead, int use_bulk, long batch, const int *__restrict__ index_list,
+                   int tail, int **__restrict__ dipiv, int *__restrict__ dinfo, unsigned short *__restrict__ sinv_w)
 {
+    // tail = 1 (four-warp CTAs, at most 96 rows below the slab's block row): the slab's own panel is factored here, from
+    // the accumulators, instead of going to HBM and back through a panel kernel (see the end of the kernel).
     // ahead: chunks in flight (1 .. RING-1); a ring slot is refilled RING - ahead chunks after its last use.
     // finish = 1: second visit of the slab that holds the LAST, narrower panel of a wide matrix
     // (32J < min(m,n) < min(n, 32J+32)): its columns right of the panel still need that panel's step.
@@ -1510,7 +1522,75 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
         }
     }
 
+    // ---- fused tail: this slab's panel, factored where it already is -------------------------------------------------
+    // The updated rows below the block row ARE the next panel. Instead of storing them and launching a panel kernel that
+    // loads them again, the CTA writes them into a shared-memory image (the ring is free now) and runs the resident-block
+    // factorisation of lu_chain.cuh on it: warp 0 = single-warp pivot chains, warps 1..3 = permutation, block-row solve and
+    // rank-8 DMMA updates. Outputs as panel_chain_kernel's (factors in final row order, pivots, step permutation record,
+    // info). Three launches and three slab round trips fewer at n = 128 -- and MEASURED SLOWER (same box, 50000 x 128^2:
+    // 8.99 ms off, 9.69 ms for the 33..96-row panels, 10.28 ms with the last panel too; n = 96: 4.98 / 5.39 / 5.98): this
+    // kernel keeps four CTAs, i.e. four pivot chains, per SM where the panel kernels keep 8..12, and chain throughput is
+    // chains in flight / ~850 cycles per column; the overlap with the other CTAs' DMMA phases does not make up for it.
+    // Kept behind magma_b200_set_fused_tail (default 0) with its parity tests.
+    if (NW == 4 && tail && !finish && c0 < mn) {
+        constexpr int LDV = 98;  // at most 96 rows (the driver's condition)
+        static_assert(sizeof(TailSmem) <= sizeof(double) * 32 * LL_LDU, "tail scratch fits Us");
+        static_assert(NW != 4 || 32 * LDV <= RING * 8 * LDR, "panel image fits the ring");
+        __syncthreads();  // every warp is past its last ring pass and solve: the staging region is free
+        TailSmem &P = *reinterpret_cast<TailSmem *>(S.Us);
+        double *V = S.ring;
+        const int jb = (mn - c0) < 32 ? (mn - c0) : 32;
+        const int mp = m - c0;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int row = 8 * (w + NW * a) + g;
+            if (row >= c0 && row < m) {
+                double *vp = V + (2 * q) * LDV + (row - c0);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int col = 8 * c + 2 * q;
+                    if (col < jb) vp[(8 * c) * LDV] = acc[a][c][0];
+                    if (col + 1 < jb) vp[(8 * c + 1) * LDV] = acc[a][c][1];
+                }
+                if (jb < nc) {  // wide last panel: the columns right of it go back as they are (the finish pass takes them)
+                    double *dst = A + row + (size_t)(c0 + 2 * q) * ld;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int col = 8 * c + 2 * q;
+                        if (col >= jb && col < nc) dst[(size_t)(8 * c) * ld] = acc[a][c][0];
+                        if (col + 1 >= jb && col + 1 < nc) dst[(size_t)(8 * c + 1) * ld] = acc[a][c][1];
+                    }
+                }
+            }
+        }
+        if (tid == 0) {
+            P.info = 0;
+            P.nmoves = 0;
+        }
+        P.perm[tid] = (unsigned char)tid;  // T = 128
+        __syncthreads();
+        factor_view<LDV, true, 3>(P, V, mp, jb, 0, nullptr, 0, tid, lane, w);
+        __syncthreads();
+        double *Ap = A + c0 + (size_t)c0 * ld;
+        if (bulk_ok) {
+            f_fence_async_smem();
+            __syncthreads();
+            if (w == 0 && lane < jb) f_bulk_store(Ap + (size_t)lane * ld, &V[lane * LDV], (unsigned)mp * 8u);
+        } else {
+            for (int c = w; c < jb; c += NW)
+                for (int r = lane; r < mp; r += 32) Ap[r + (size_t)c * ld] = V[c * LDV + r];
+        }
+        if (tid < jb) dipiv[b][c0 + tid] = c0 + P.ipiv[tid] + 1;
+        {
+            unsigned short *sv = sinv_w + ((size_t)slot * sinv_blocks + J) * sinv_rows + c0;
+            for (int p = tid; p < mp; p += T) sv[p] = (unsigned short)(c0 + P.perm[p]);
+        }
+        if (tid == 0 && P.info && dinfo[b] == 0) dinfo[b] = c0 + P.info;  // J > 0: earlier panels have priority
+        if (bulk_ok && w == 0) f_bulk_commit_wait();
+        return;
+    }
     // ---- rows that are not U yet go back, current order ---------------------------------------------------------
+    const int cfirst = cb;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int row = 8 * (w + NW * a) + g;
@@ -1519,16 +1599,17 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int col = 8 * c + 2 * q;
-                if (col >= cb && col < nc) dst[(size_t)(8 * c) * ld] = acc[a][c][0];
-                if (col + 1 >= cb && col + 1 < nc) dst[(size_t)(8 * c + 1) * ld] = acc[a][c][1];
+                if (col >= cfirst && col < nc) dst[(size_t)(8 * c) * ld] = acc[a][c][0];
+                if (col + 1 >= cfirst && col + 1 < nc) dst[(size_t)(8 * c + 1) * ld] = acc[a][c][1];
             }
         }
     }
 }
 
 template <int NW>
-magma_int_t launch_left_update(const Dims &d, double **dA, const unsigned short *sinv, int sinv_rows, int sinv_blocks,
-                               int J, int finish, long batch, const int *il, cudaStream_t s)
+magma_int_t launch_left_update(const Dims &d, double **dA, unsigned short *sinv, int sinv_rows, int sinv_blocks,
+                               int J, int finish, long batch, const int *il, cudaStream_t s, int tail = 0, int **dipiv = nullptr,
+                               int *dinfo = nullptr)
 {
     const size_t smem = sizeof(LeftSmem<NW>);
     static DevOnce once;
@@ -1545,7 +1626,8 @@ magma_int_t launch_left_update(const Dims &d, double **dA, const unsigned short 
         const char *e = getenv("MB200_LL_BULK");  // 0: LDGSTS staging instead of TMA bulk copies (A/B runs)
         use_bulk = e ? atoi(e) : 1;  // bit 0: L chunks and slab (n = 512: 30.8 -> 27.2 ms), bit 1: L_KK too (32 copies of 256 B: 28.7 ms, off)
     }
-    left_update_kernel<NW><<<(unsigned)batch, NW * 32, smem, s>>>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, ahead, use_bulk, batch, il);
+    left_update_kernel<NW><<<(unsigned)batch, NW * 32, smem, s>>>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, ahead, use_bulk, batch, il,
+                                                                  NW == 4 ? tail : 0, dipiv, dinfo, sinv);
     count_launch();
     MB200_CHECK_LAUNCH("left_update_kernel");
     return 0;
@@ -1790,22 +1872,28 @@ magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, i
     const int max_mn = max_m < max_n ? max_m : max_n;
     const int sinv_rows = ((max_m + 31) / 32) * 32, sinv_blocks = (max_mn + 31) / 32;
     const int slabs = (max_n + 31) / 32;
-    auto left = [&](int J, int finish) -> magma_int_t {
-        if (max_m <= 128) return launch_left_update<4>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, batch, il, s);
+    auto left = [&](int J, int finish, int tail = 0) -> magma_int_t {
+        if (max_m <= 128) return launch_left_update<4>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, batch, il, s, tail, dipiv, dinfo);
         return (max_m <= 256) ? launch_left_update<8>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, batch, il, s)
                               : launch_left_update<16>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, batch, il, s);
     };
     for (int J = 0; J < slabs; ++J) {
         magma_int_t rc = 0;
-        if (J > 0) rc = left(J, 0);
-        if (rc != 0) return rc;
         const int j = 32 * J;
+        // fused tail (left_update_kernel<4>): the panel of slab J is factored by the CTA that has just updated it.
+        // g_fused_tail: 0 off (default, see the kernel), 1 panels of 33..96 rows, 2 every panel of at most 96 rows
+        const int Tj = ((max_m - j + 31) / 32) * 32;
+        const bool tail = J > 0 && j < max_mn && !nopiv && max_m <= 128 && Tj <= 96 && g_fused_tail > 0 && (g_fused_tail >= 2 || Tj > 32);
+        if (J > 0) rc = left(J, 0, tail ? 1 : 0);
+        if (rc != 0) return rc;
         if (j < max_mn) {
-            const int T = ((max_m - j + 31) / 32) * 32;
+            const int T = Tj;
             // single-warp pivot chains (panel_chain_kernel, lu_fused.cu) for panels of 33..128 rows (g_chain_panel = 3: rows >
             // 128 - 32 * level). Same box, panel_kernel -> chain kernel: n = 128 9.72 -> 9.11 ms, n = 96 5.28 -> 5.00,
             // n = 64 4.36 -> 4.25, n = 48 3.79 -> 3.66. The last <= 32-row panel stays with panel_kernel (level 4 costs 0.2-0.4 ms).
-            if (!nopiv && T <= 128 && g_chain_panel > 0 && T > 128 - 32 * g_chain_panel) {
+            if (tail) {
+                // factored inside left_update_kernel
+            } else if (!nopiv && T <= 128 && g_chain_panel > 0 && T > 128 - 32 * g_chain_panel) {
                 if ((rc = panel_chain_launch(d, dA, dipiv, dinfo, j, T, batch, il, s, sinv, sinv_rows, sinv_blocks)) != 0) return rc;
             } else {
                 launch_panel32(d, dA, dipiv, dinfo, recs, j, T, batch, il, s, sinv, sinv_rows, sinv_blocks, nopiv);

@@ -11,6 +11,7 @@ namespace mb200 {
 std::atomic<int64_t> g_launches{0};
 int g_tier = 0;
 int g_chain_panel = 3;
+int g_fused_tail = 0;
 static std::atomic<int> g_init_count{0};
 
 #ifdef MB200_INTERPOSE
@@ -460,4 +461,5 @@ int64_t magma_b200_launch_count(void) { return g_launches.load(); }
 void magma_b200_set_tier(int tier) { g_tier = tier; }
 void magma_b200_set_small_rows(int rows) { g_small_rows = rows; }
 void magma_b200_set_chain_panel(int on) { g_chain_panel = on; }
+void magma_b200_set_fused_tail(int level) { g_fused_tail = level; }
 }  // extern "C"

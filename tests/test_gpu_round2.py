@@ -766,3 +766,56 @@ def test_register_tier_layout_switches_n32(gpu_queue, rows):
         check_against_oracle(gpu_queue, A0, 32)
     finally:
         mb.set_small_rows(0)
+
+
+@pytest.mark.parametrize("level", [0, 1, 2])
+@pytest.mark.parametrize("m,n,batch", [(128, 128, 7), (100, 100, 5), (97, 97, 5), (128, 40, 5), (120, 200, 4), (127, 96, 4), (96, 96, 5),
+                                       (64, 64, 6), (65, 90, 4), (50, 45, 5), (45, 128, 4), (128, 127, 3), (101, 67, 4)])
+def test_fused_tail_switch(gpu_queue, level, m, n, batch):
+    """Left-looking driver, at most 128 rows: panels factored in the tail of the slab kernel (off by default: slower),
+    every switch level gives the oracle's bits (square, tall, wide with a narrow last panel, odd sizes: plain-store path)."""
+    mb.set_fused_tail(level)
+    try:
+        A0, _ = oracle.random_batch(batch, m, n)
+        check_against_oracle(gpu_queue, A0, m)
+    finally:
+        mb.set_fused_tail(0)
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_fused_tail_structured_and_vbatched(gpu_queue, level):
+    import torch
+    mb.set_fused_tail(level)
+    try:
+        rng = np.random.default_rng(19)
+        n = 128
+        mats = [np.zeros((n, n)), np.ones((n, n)), np.eye(n), np.fliplr(np.eye(n)), rng.integers(-3, 4, size=(n, n)).astype(float)]
+        Z = rng.random((n, n)); Z[:, 40] = 0.0; Z[:, 100] = 0.0; mats.append(Z)
+        Z2 = rng.random((n, n)); Z2[n // 2:, :] = Z2[:n - n // 2, :]; mats.append(Z2)
+        check_against_oracle(gpu_queue, np.stack(mats), n)
+        # variable sizes inside the <= 128-row classes: members shorter and narrower than the class maximum
+        batch = 40
+        ms = rng.integers(33, 129, size=batch).astype(np.int32)
+        ns = rng.integers(33, 129, size=batch).astype(np.int32)
+        ms[0], ns[0] = 128, 128
+        lds = ms.copy()
+        mats = [oracle.random_batch(1, int(ms[b]), int(ns[b]))[0][0] for b in range(batch)]  # (n, ld = m)
+        offs = np.cumsum([0] + [x.size for x in mats])
+        flat = torch.from_numpy(np.concatenate([x.reshape(-1) for x in mats])).cuda()
+        aptr = torch.tensor([flat.data_ptr() + int(offs[b]) * 8 for b in range(batch)], dtype=torch.int64, device="cuda")
+        kmax = int(np.minimum(ms, ns).max())
+        ip = torch.zeros((batch, kmax), dtype=torch.int32, device="cuda")
+        ipp = torch.tensor([ip.data_ptr() + b * kmax * 4 for b in range(batch)], dtype=torch.int64, device="cuda")
+        info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+        dm, dn, dl = (torch.from_numpy(x).cuda() for x in (ms, ns, lds))
+        assert mb.magma_dgetrf_vbatched(dm, dn, aptr, dl, ipp, info, batch, gpu_queue) == 0
+        gpu_queue.sync()
+        out, iph = flat.cpu().numpy(), ip.cpu().numpy()
+        for b in range(batch):
+            m, nn = int(ms[b]), int(ns[b])
+            ref = mats[b].copy().reshape(1, nn, m)
+            ipr, infr = oracle.getrf_batched(ref, m)
+            assert np.array_equal(iph[b, :min(m, nn)], ipr[0]), (b, m, nn)
+            assert np.array_equal(out[offs[b]:offs[b + 1]].reshape(1, nn, m), ref), (b, m, nn)
+    finally:
+        mb.set_fused_tail(0)

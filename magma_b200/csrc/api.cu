@@ -671,7 +671,7 @@ static void ensure_aux(magma_queue_t queue)
     cudaGetDevice(&prev);
     if (prev != q->device) cudaSetDevice(q->device);
     for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&q->aux_stream[i], cudaStreamNonBlocking);
-    for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&q->aux_event[i], cudaEventDisableTiming);
+    for (int i = 0; i < 12; ++i) cudaEventCreateWithFlags(&q->aux_event[i], cudaEventDisableTiming);
     q->aux_ready = true;
     if (prev != q->device) cudaSetDevice(prev);
 }
@@ -692,7 +692,16 @@ static magma_int_t host_pipeline(bool solve, int m, int n, int nrhs, double *hA,
     long chunk = (long)std::max<size_t>(1, ((size_t)g_host_chunk_mb << 20) / per_mat);
     if (chunk > batch) chunk = batch;
     const size_t stride = ((per_mat * chunk + 64 + 255) / 256) * 256;
-    char *dev = (char *)queue_dscratch(queue, 2 * stride, 0);
+    // staging buffers in the ring (MB200_HOST_NBUF = 2..4 for sweeps). Measured on the headline step, same box: 2 / 3 / 4
+    // buffers 50.9 / 50.8 / 50.7 ms against 44.9 ms for the bare copies: the ring depth is not what separates them
+    static int nbuf = 0;
+    if (nbuf == 0) {
+        const char *e = getenv("MB200_HOST_NBUF");
+        nbuf = e ? atoi(e) : 2;
+        if (nbuf < 2) nbuf = 2;
+        if (nbuf > 4) nbuf = 4;
+    }
+    char *dev = (char *)queue_dscratch(queue, (size_t)nbuf * stride, 0);
     if (!dev) {
         magma_xerbla(solve ? "magma_b200_dgesv_batched_host" : "magma_b200_dgetrf_batched_host", -MAGMA_ERR_DEVICE_ALLOC);
         return MAGMA_ERR_DEVICE_ALLOC;
@@ -700,14 +709,14 @@ static magma_int_t host_pipeline(bool solve, int m, int n, int nrhs, double *hA,
     cudaStream_t sc = MB200_Q(queue)->stream;
     cudaStream_t sh = MB200_Q(queue)->aux_stream[0];  // H2D
     cudaStream_t sd = MB200_Q(queue)->aux_stream[1];  // D2H
-    cudaEvent_t *ev_in = MB200_Q(queue)->aux_event;        // [2] H2D done
-    cudaEvent_t *ev_done = MB200_Q(queue)->aux_event + 2;  // [2] compute done
-    cudaEvent_t *ev_out = MB200_Q(queue)->aux_event + 4;   // [2] D2H done (buffer free)
+    cudaEvent_t *ev_in = MB200_Q(queue)->aux_event;        // [4] H2D done
+    cudaEvent_t *ev_done = MB200_Q(queue)->aux_event + 4;  // [4] compute done
+    cudaEvent_t *ev_out = MB200_Q(queue)->aux_event + 8;   // [4] D2H done (buffer free)
     magma_int_t rc = 0;
     long it = 0;
     for (long off = 0; off < batch; off += chunk, ++it) {
         const long cnt = std::min<long>(chunk, batch - off);
-        const int bsel = (int)(it & 1);
+        const int bsel = (int)(it % nbuf);
         char *base = dev + (size_t)bsel * stride;
         double *dAm = (double *)base;
         double *dBm = dAm + a_elems * chunk;
@@ -719,12 +728,12 @@ static magma_int_t host_pipeline(bool solve, int m, int n, int nrhs, double *hA,
         double **pA = (double **)pbase;
         double **pB = pA + chunk;
         int **pP = (int **)(pB + chunk);
-        if (it >= 2) cudaStreamWaitEvent(sh, ev_out[bsel], 0);  // buffer reuse
+        if (it >= nbuf) cudaStreamWaitEvent(sh, ev_out[bsel], 0);  // buffer reuse
         cudaMemcpyAsync(dAm, hA + (size_t)off * a_elems, a_elems * 8 * cnt, cudaMemcpyHostToDevice, sh);
         if (solve) cudaMemcpyAsync(dBm, hB + (size_t)off * b_elems, b_elems * 8 * cnt, cudaMemcpyHostToDevice, sh);
         cudaEventRecord(ev_in[bsel], sh);
         cudaStreamWaitEvent(sc, ev_in[bsel], 0);
-        if (it >= 2) cudaStreamWaitEvent(sc, ev_out[bsel], 0);
+        if (it >= nbuf) cudaStreamWaitEvent(sc, ev_out[bsel], 0);
         set_pointer_launch((void **)pA, (char *)dAm, 8, lda, 0, 0, (long)a_elems, cnt, sc);
         set_pointer_launch((void **)pP, (char *)dip, 4, 1, 0, 0, mn, cnt, sc);
         if (solve) {

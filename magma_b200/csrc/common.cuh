@@ -33,7 +33,7 @@ struct magma_queue {
     size_t hscratch_bytes;
     // host front ends: two extra streams + events for the H2D / compute / D2H pipeline
     cudaStream_t aux_stream[2];
-    cudaEvent_t aux_event[8];
+    cudaEvent_t aux_event[12];
     bool aux_ready;
 };
 #ifdef MB200_INTERPOSE

@@ -147,6 +147,9 @@ __device__ __forceinline__ void panel_chain(SM &S, const unsigned vbase, const i
 #pragma unroll
         for (int c = 0; c < 8; ++c) a[k][c] = (valid && c < jb) ? f_lds(cbase + (unsigned)(c * LD + r) * 8u) : 0.0;
     }
+    // every lane has read its rows before any lane stores a pivot row's U part into another lane's row (same warp, in
+    // program order anyway; the barrier states it for compute-sanitizer's racecheck)
+    __syncwarp();
     const bool lane0 = lane == 0;
     int info = 0;
     int cnt = 0;  // moves recorded so far (warp-uniform)
@@ -288,6 +291,9 @@ __device__ __forceinline__ void panel_chain_rolled(SM &S, const unsigned vbase, 
 #pragma unroll
         for (int c = 0; c < 8; ++c) a[k][c] = (valid && c < jb) ? f_lds(cbase + (unsigned)(c * LD + r) * 8u) : 0.0;
     }
+    // every lane has read its rows before any lane stores a pivot row's U part into another lane's row (same warp, in
+    // program order anyway; the barrier states it for compute-sanitizer's racecheck)
+    __syncwarp();
     const bool lane0 = lane == 0;
     const unsigned rowb = (unsigned)(lane + 32 * k0) * 8u;  // byte offset of this lane's slot-0 row inside a column
     int info = 0;

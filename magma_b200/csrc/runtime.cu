@@ -240,7 +240,7 @@ void magma_queue_destroy_internal(magma_queue_t q, const char *func, const char 
     cudaStreamSynchronize(q->stream);
     if (q->aux_ready) {
         for (int i = 0; i < 2; ++i) cudaStreamDestroy(q->aux_stream[i]);
-        for (int i = 0; i < 8; ++i) cudaEventDestroy(q->aux_event[i]);
+        for (int i = 0; i < 12; ++i) cudaEventDestroy(q->aux_event[i]);
     }
     for (int i = 0; i < 2; ++i)
         if (q->dscratch[i]) cudaFree(q->dscratch[i]);

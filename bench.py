@@ -413,11 +413,24 @@ def main():
                        "parallelism": f"batch sharded by matrix index over {world} GPU(s), no collective",
                        "l2": "inputs larger than L2"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(gpu_launches),
-            "clocks": clocks.summary(), "peaks": peaks, "sweep": sweep, "strong": strong, "ref_gpu": ref_gpu,
+            "clocks": clocks.summary(), "peaks": peaks, "metric_sizes": metric_sizes(sweep), "sweep": sweep, "strong": strong,
+            "ref_gpu": ref_gpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def metric_sizes(sweep):
+    """BASELINE.json's metric names dgetrf at n = 32 / 128 / 512: their rows of the sweep, pulled up beside the headline
+    (which is BASELINE configs[1], gesv n = 16) so that no reader has to dig for them."""
+    out = {}
+    for key, tag in (("n32_batch1e4", "C1 "), ("n32_batch1e6", "C1b "), ("n128_batch5e4", "C3 "), ("n512_batch4e3", "C5 ")):
+        for r in sweep:
+            if r["config"].startswith(tag):
+                out[key] = {"ms": r["ms"], "gflops_per_gpu": r.get("gflops_per_gpu"), "roofline_gflops": r.get("roofline_gflops"),
+                            "frac_of_roofline": r.get("frac_of_roofline"), "bound": r.get("bound", "min(hbm, fp64)")}
+    return out
 
 
 def run_sweep(mb, torch, np, q, local, rank, world, barrier, max_over_ranks, sum_over_ranks, hbm_peak, fp64_peak):
@@ -542,6 +555,7 @@ def run_sweep(mb, torch, np, q, local, rank, world, barrier, max_over_ranks, sum
         torch.cuda.empty_cache()
 
     getri("F1 dgetri_outofplace_batched n=64 batch=100000", 64, 100_000)
+    getri("F1b dgetri_outofplace_batched n=32 batch=400000", 32, 400_000)
 
     # F2: LU without pivoting, n = 128 (diagonally dominant inputs: dlarnv + n on the diagonal)
     def nopiv(name, n, batch, reps=5):

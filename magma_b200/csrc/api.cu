@@ -31,10 +31,10 @@ constexpr long MAX_CHUNK = 1L << 24;
 
 // Largest dimension routed to the register-file tier (lu_mid.cu); above it the blocked tier runs.
 // Measured crossover on B200 (tools/gpu_probe.py, PROBE_MID): see DESIGN.md "tiers and crossovers".
-int g_mid_max = 128;
-int g_fused_max = 0;  // largest dimension routed to the single-launch shared-memory tier (lu_fused.cu); 0 = off (default:
+std::atomic<int> g_mid_max{128};
+std::atomic<int> g_fused_max{0};  // largest dimension routed to the single-launch shared-memory tier (lu_fused.cu); 0 = off (default:
                       // measured slower than the slab drivers)
-int g_host_chunk_mb = 64;  // host front ends: payload per staging buffer (MB200_HOST_CHUNK_MB overrides, for sweeps)
+std::atomic<int> g_host_chunk_mb{64};  // host front ends: payload per staging buffer (MB200_HOST_CHUNK_MB overrides, for sweeps)
 
 }  // namespace
 
@@ -395,7 +395,7 @@ static magma_int_t vbatched_run(magma_int_t *m, magma_int_t *n, int max_m, int m
     long cnt[7];
     for (int c = 0; c < 7; ++c) cnt[c] = known ? known[c] : batch;
     if (!known) cudaMemsetAsync(lists, 0xFF, sizeof(int) * 7 * (size_t)batch, s);
-    const int mid_max = (g_tier == 2) ? 32 : g_mid_max;
+    const int mid_max = (g_tier == 2) ? 32 : g_mid_max.load();
     vbatched_partition_launch(m, n, batch, lists, counts, mid_max, s);
     magma_int_t rc = 0;
     if (cnt[0] > 0) {
@@ -493,7 +493,7 @@ magma_int_t magma_dgetrf_vbatched(magma_int_t *m, magma_int_t *n, double **dA_ar
         return 0;
     }
     // bin sizes as the partition kernel will produce them (classes above mid_max fall into the last bin)
-    const int mid_max = (g_tier == 2) ? 32 : g_mid_max;
+    const int mid_max = (g_tier == 2) ? 32 : g_mid_max.load();
     int known[7] = {h[5], h[8], h[9], h[10], h[11], h[12], 0};
     // classes above mid_max belong to the blocked bins (all three are <= 256, so they join bin 4)
     if (mid_max < 64) { known[4] += known[1]; known[1] = 0; }

@@ -47,8 +47,8 @@ QState *qstate(magma_queue_t q);  // finds or creates the entry; refreshes strea
 namespace mb200 {
 
 extern std::atomic<int64_t> g_launches;
-extern int g_tier;  // 0 auto, 1 force small/register tier, 2 force blocked tier
-extern int g_small_rows;  // register tier: rows per lane, 0 = tuned default
+extern std::atomic<int> g_tier;  // 0 auto, 1 force small/register tier, 2 force blocked tier
+extern std::atomic<int> g_small_rows;  // register tier: rows per lane, 0 = tuned default
 
 // ---- B200 tuning table: the ONE place tier boundaries and panel widths are written down. The drivers below and the
 // reference-named getters (magma_get_dgetrf_batched_nbparam / _ntcol, magma_b200_get_dgetrf_batched_crossover) all
@@ -161,8 +161,8 @@ long rcp_selftest_run(long n, cudaStream_t s);
 // lu_fused.cu: 32-column panel by single-warp pivot chains (panels of at most 128 rows); -100 = not covered
 magma_int_t panel_chain_launch(const Dims &d, double **dA, int **dipiv, int *dinfo, int j, int T, long batch, const int *il,
                                cudaStream_t s, unsigned short *sinv, int sinv_rows, int sinv_blocks);
-extern int g_fused_tail;   // left-looking driver, at most 128 rows: panels factored in the slab kernel's tail (0 off = default: measured slower; 1: 33..96 rows, 2: <= 96 rows)
-extern int g_chain_panel;  // level L > 0: panels of (128 - 32 L, 128] rows go to panel_chain_launch (default 3); 0: panel_kernel
+extern std::atomic<int> g_fused_tail;   // left-looking driver, at most 128 rows: panels factored in the slab kernel's tail (0 off = default: measured slower; 1: 33..96 rows, 2: <= 96 rows)
+extern std::atomic<int> g_chain_panel;  // level L > 0: panels of (128 - 32 L, 128] rows go to panel_chain_launch (default 3); 0: panel_kernel
 
 // lu_blocked.cu: blocked right-looking LU for any m x n (two kernels per panel step).
 // `workspace` must hold lu_blocked_workspace_bytes(batch) bytes (one 512-byte pivot record per matrix).

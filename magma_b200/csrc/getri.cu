@@ -17,7 +17,7 @@
 
 namespace mb200 {
 
-int g_getri_fused = 1;  // 0: identity + getrs for every n (A/B runs, tests)
+std::atomic<int> g_getri_fused{1};  // 0: identity + getrs for every n (A/B runs, tests)
 
 namespace {
 

@@ -27,7 +27,7 @@
 
 namespace mb200 {
 
-int g_small_rows = 0;  // 0 = tuned default, 1 / 2 = force rows per lane (tests, tuning sweeps)
+std::atomic<int> g_small_rows{0};  // 0 = tuned default, 1 / 2 = force rows per lane (tests, tuning sweeps)
 
 namespace {
 

@@ -9,9 +9,9 @@
 
 namespace mb200 {
 std::atomic<int64_t> g_launches{0};
-int g_tier = 0;
-int g_chain_panel = 3;
-int g_fused_tail = 0;
+std::atomic<int> g_tier{0};
+std::atomic<int> g_chain_panel{3};
+std::atomic<int> g_fused_tail{0};
 static std::atomic<int> g_init_count{0};
 
 #ifdef MB200_INTERPOSE

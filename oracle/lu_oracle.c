@@ -23,10 +23,11 @@
  *     a(i,j) <- fma(-l(i,k), u(k,j), a(i,j))   for k = 0,1,...,min(i,j)-1 in increasing k,
  * multipliers are l(i,k) = a(i,k) * (1/pivot) with an IEEE-correct reciprocal. Any blocked
  * variant that applies the same per-element fma sequence produces bit-identical factors; the
- * CUDA kernels of this repo that use DFMA are written to do exactly that, so the GPU tests can
- * demand bit equality against this file, not just a backward-error bound. Kernels that use the
- * FP64 tensor pipe (DMMA) accumulate four products per instruction and are held to identical
- * pivots + the reference testers' 30*eps backward-error bound instead.
+ * CUDA kernels of this repo are written to do exactly that, so the GPU tests demand bit
+ * equality against this file, not just a backward-error bound. That includes the kernels on the
+ * FP64 tensor pipe: mma.sync.m8n8k4.f64 (DMMA) was measured on the B200 to equal a chain of four
+ * FMAs with k increasing (tools/dmma_probe.cu, 262144 of 262144 outputs), and the kernels feed it
+ * the operands in canonical k order.
  *
  * The host LAPACK the reference's testers call (third-party; OpenBLAS 0.3.31.dev bundled with
  * scipy in this image) is NOT restated here: tests/ pin this oracle against it (identical

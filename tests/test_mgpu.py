@@ -76,7 +76,10 @@ def _worker(rank, world, port, out_dir):
 
 def test_two_rank_gloo_sharded_run(tmp_path):
     import torch.multiprocessing as mp
-    port = 29500 + (os.getpid() % 2000)
+    import socket
+    with socket.socket() as sk:  # a port the kernel says is free right now (a pid-derived one collided once with a live process)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     ok = np.load(os.path.join(tmp_path, "ok.npy"))
     assert ok.all(), ok

@@ -1131,7 +1131,11 @@ struct TailSmem {
     unsigned char mdst[16], msrc[16], perm[128];
 };
 
-template <int NW>
+// ANY = false: the kernel as tuned for 16-byte aligned matrices (TMA staging only where every column starts on a 16-byte
+// boundary and has an even number of rows, cp.async otherwise). ANY = true: TMA staging for any alignment through
+// parity-shifted shared-memory columns (below); chosen by the host for variable-size batches and for fixed sizes with an odd
+// m or ldda. Two instantiations because both paths in one kernel cost the aligned case 1.3-2.6% (n = 128, n = 512).
+template <int NW, bool ANY>
 __global__ void __launch_bounds__(NW * 32, NW == 16 ? 1 : (NW == 8 ? 2 : 4))
 left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__restrict__ sinv_g, int sinv_rows,
                    int sinv_blocks, int J, int finish, int ahead, int use_bulk, long batch, const int *__restrict__ index_list,
@@ -1171,7 +1175,17 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
     constexpr int LDR = LeftSmem<NW>::LDR;
     static_assert(sizeof(double) * 32 * LDR <= sizeof(double) * (2 * 32 * LL_LDU + 32 * 33 + RING * 8 * LDR), "slab staging region");
     const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-    const bool bulk_ok = vec_ok && ((m & 1) == 0) && (use_bulk != 0);  // 16-byte aligned columns of a multiple of 16 bytes
+    const bool aligned_ok = vec_ok && ((m & 1) == 0);  // 16-byte aligned columns of a multiple of 16 bytes (TMA stores)
+    // TMA staging works for ANY alignment: a column whose first wanted element sits at an odd double index is copied from
+    // one element earlier (always inside the matrix or, for column 0 of a matrix at 8 mod 16, inside its allocation, whose
+    // start is 256-byte aligned) and lands one slot lower in shared memory, so that source and destination are both
+    // 16-byte aligned; readers add the column's parity to the row index. An odd remainder row goes by a plain copy.
+    // (Half of a vbatched batch with ldda = n has an odd leading dimension, half of the rest an 8-mod-16 base: BASELINE
+    // config 4 ran three quarters of its matrices through the 8-byte cp.async paths, 58.3 ms against 49.7 ms all-aligned.)
+    const bool bulk_ok = ANY ? ((use_bulk & 1) != 0) : (aligned_ok && use_bulk != 0);
+    // parity of the double index of element (0, col); from A and ld each time, so that nothing extra stays live in the
+    // update loop (the aligned case must keep the register allocation it had: C3 / C5 are all-aligned)
+    auto colpar = [&](int col) { return (int)(((reinterpret_cast<uintptr_t>(A) >> 3) + (uintptr_t)(col & ld)) & 1u); };
     if (tid == 0) {
         for (int i = 0; i < RING; ++i) {
             ll_mbar_init(&S.full[i], T);
@@ -1184,7 +1198,7 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
     __syncthreads();
     // ---- the slab: one TMA bulk copy per column into the staging region, in flight while the maps are built ------
     double *const stage = S.Us;
-    if (bulk_ok && tid < 32) {
+    if (!ANY && bulk_ok && tid < 32) {
         if (tid == 0) {
             int ncopy = 0;
             for (int cc = 0; cc < 32; ++cc) ncopy += (cc >= cb && cc < nc) ? 1 : 0;
@@ -1194,6 +1208,23 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
                          : "memory");
         }
         if (tid >= cb && tid < nc) ll_bulk_load(stage + tid * LDR, A + (size_t)(c0 + tid) * ld, (unsigned)m * 8u, &S.stbar);
+    }
+    if (ANY && bulk_ok && tid < 32) {
+        // column tid of the slab: rows [-p, m) -> slots [0, m + p), p = its parity; an even number of them by TMA
+        const bool mine = tid >= cb && tid < nc;
+        const int p = colpar(c0 + tid);
+        const unsigned ce = mine ? (unsigned)((m + p) & ~1) : 0u;
+        const unsigned total = __reduce_add_sync(FULLM, ce);
+        if (tid == 0)
+            asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(&S.stbar)),
+                         "r"(total * 8u)
+                         : "memory");
+        if (mine) {
+            const double *colp = A + (size_t)(c0 + tid) * ld;
+            if (ce) ll_bulk_load(stage + tid * LDR, colp - p, ce * 8u, &S.stbar);
+            if ((unsigned)(m + p) > ce) stage[tid * LDR + m - 1 + p] = colp[m - 1];  // visible after the barriers below
+        }
     }
     // ---- row maps ----------------------------------------------------------------------------------------
     unsigned short(*sinv_s)[T] = S.sinv_s;
@@ -1232,10 +1263,24 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
                 // as a transaction count on top of the T plain arrivals below (LDGSTS needed up to four copies plus
                 // address arithmetic from every thread: 20% of the kernel's stall samples sat in this block)
                 // (one copy per LANE: issued from a loop on one thread, the copies of a step cost that warp ~2k cycles)
+                // Column kk: rows [rlo - p, m) -> slots [rlo, m + p), p = the column's parity (rlo is even).
                 if (tid < 8) {
-                    const unsigned bytes = (unsigned)(m - rlo) * 8u;
-                    if (tid == 0) ll_mbar_expect_tx(&S.full[slot_r], 8u * bytes);
-                    ll_bulk_load(dst + tid * LDR + rlo, colbase + (size_t)tid * ld + rlo, bytes, &S.full[slot_r]);
+                    if (!ANY) {  // every column starts on a 16-byte boundary and has an even number of rows
+                        const unsigned bytes = (unsigned)(m - rlo) * 8u;
+                        if (tid == 0) ll_mbar_expect_tx(&S.full[slot_r], 8u * bytes);
+                        ll_bulk_load(dst + tid * LDR + rlo, colbase + (size_t)tid * ld + rlo, bytes, &S.full[slot_r]);
+                    } else {
+                        // column kk = tid: rows [rlo - p, m) -> slots [rlo, m + p), p = the column's parity (32 K + 8 ch is even)
+                        const int p = colpar(tid);
+                        const unsigned ce = (unsigned)((m - rlo + p) & ~1);
+                        if (tid == 0) {
+                            const unsigned c0e = (unsigned)((m - rlo + colpar(0)) & ~1), c1e = (unsigned)((m - rlo + colpar(1)) & ~1);
+                            ll_mbar_expect_tx(&S.full[slot_r], 4u * (c0e + c1e) * 8u);  // the eight columns alternate (or share) a parity
+                        }
+                        const double *colp = colbase + (size_t)tid * ld;
+                        if (ce) ll_bulk_load(dst + tid * LDR + rlo, colp + rlo - p, ce * 8u, &S.full[slot_r]);
+                        if ((unsigned)(m - rlo + p) > ce) cp_async8(dst + tid * LDR + m - 1 + p, colp + m - 1, true);
+                    }
                 }
             } else if (rlo < m) {
                 if (vec_ok) {
@@ -1305,10 +1350,11 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             const int row = 8 * (w + NW * a) + g;
             const bool rok = row < m;
             const double *sp = stage + (rok ? (int)S.src[row] : 0) + (2 * q) * LDR;
+            const int p0 = ANY ? colpar(0) : 0, p1 = ANY ? colpar(1) : 0;  // even / odd columns of the slab (c0 is even)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                acc[a][c][0] = rok ? sp[(8 * c) * LDR] : 0.0;
-                acc[a][c][1] = rok ? sp[(8 * c + 1) * LDR] : 0.0;
+                acc[a][c][0] = rok ? sp[(8 * c) * LDR + p0] : 0.0;
+                acc[a][c][1] = rok ? sp[(8 * c + 1) * LDR + p1] : 0.0;
             }
         }
         __syncthreads();  // the staging region is free: its parts take their own roles
@@ -1466,6 +1512,12 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             const int row = 8 * (w + NW * a) + g;
             roff[a] = (row < m) ? (int)S.rmap[K][row] : 32 * (K + 1);  // rows past m: any row of the chunk
         }
+        // chunks that came in by TMA sit one slot lower in the columns of odd parity; this lane reads columns 4 s2 + q
+        if (ANY && bulk_ok && kb == 32) {
+            const int pq = colpar(q);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) roff[a] += pq;
+        }
         auto ring_pass = [&](auto amin_c, auto aend_c) {
             constexpr int AMIN = decltype(amin_c)::value;   // first active tile slot
             constexpr int AEND = decltype(aend_c)::value;   // one past the last tile slot that has rows (< m)
@@ -1572,7 +1624,7 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
         factor_view<LDV, true, 3>(P, V, mp, jb, 0, nullptr, 0, tid, lane, w);
         __syncthreads();
         double *Ap = A + c0 + (size_t)c0 * ld;
-        if (bulk_ok) {
+        if (aligned_ok) {
             f_fence_async_smem();
             __syncthreads();
             if (w == 0 && lane < jb) f_bulk_store(Ap + (size_t)lane * ld, &V[lane * LDV], (unsigned)mp * 8u);
@@ -1586,7 +1638,7 @@ left_update_kernel(Dims d, double **__restrict__ dA, const unsigned short *__res
             for (int p = tid; p < mp; p += T) sv[p] = (unsigned short)(c0 + P.perm[p]);
         }
         if (tid == 0 && P.info && dinfo[b] == 0) dinfo[b] = c0 + P.info;  // J > 0: earlier panels have priority
-        if (bulk_ok && w == 0) f_bulk_commit_wait();
+        if (aligned_ok && w == 0) f_bulk_commit_wait();
         return;
     }
     // ---- rows that are not U yet go back, current order ---------------------------------------------------------
@@ -1612,8 +1664,11 @@ magma_int_t launch_left_update(const Dims &d, double **dA, unsigned short *sinv,
                                int *dinfo = nullptr)
 {
     const size_t smem = sizeof(LeftSmem<NW>);
-    static DevOnce once;
-    smem_optin(once, left_update_kernel<NW>, smem);
+    static DevOnce once, once_any;
+    smem_optin(once, left_update_kernel<NW, false>, smem);
+    smem_optin(once_any, left_update_kernel<NW, true>, smem);
+    // variable sizes, or a fixed size with an odd m or ldda: the any-alignment instantiation (see the kernel)
+    const bool any = d.vm != nullptr || (d.m & 1) || (d.ldda & 1);
     static int ahead = -1;
     if (ahead < 0) {
         const char *e = getenv("MB200_LL_AHEAD");  // tuning sweeps
@@ -1626,8 +1681,12 @@ magma_int_t launch_left_update(const Dims &d, double **dA, unsigned short *sinv,
         const char *e = getenv("MB200_LL_BULK");  // 0: LDGSTS staging instead of TMA bulk copies (A/B runs)
         use_bulk = e ? atoi(e) : 1;  // bit 0: L chunks and slab (n = 512: 30.8 -> 27.2 ms), bit 1: L_KK too (32 copies of 256 B: 28.7 ms, off)
     }
-    left_update_kernel<NW><<<(unsigned)batch, NW * 32, smem, s>>>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, ahead, use_bulk, batch, il,
-                                                                  NW == 4 ? tail : 0, dipiv, dinfo, sinv);
+    if (any)
+        left_update_kernel<NW, true><<<(unsigned)batch, NW * 32, smem, s>>>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, ahead, use_bulk,
+                                                                            batch, il, NW == 4 ? tail : 0, dipiv, dinfo, sinv);
+    else
+        left_update_kernel<NW, false><<<(unsigned)batch, NW * 32, smem, s>>>(d, dA, sinv, sinv_rows, sinv_blocks, J, finish, ahead, use_bulk,
+                                                                             batch, il, NW == 4 ? tail : 0, dipiv, dinfo, sinv);
     count_launch();
     MB200_CHECK_LAUNCH("left_update_kernel");
     return 0;

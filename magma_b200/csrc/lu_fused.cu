@@ -310,8 +310,11 @@ panel_chain_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, i
         }
         f_mbar_wait(&S.bar[0], 0);
     } else {
+        // any alignment: 8-byte cp.asyncs, all in flight at once (plain loads here were a chain of dependent
+        // load -> store pairs per thread: the n = 127 call spent a third of its time in them)
         for (int c = w; c < jb; c += 2)
-            for (int r = lane; r < mp; r += 32) S.V[c * LD + r] = A[r + (size_t)c * ld];
+            for (int r = lane; r < mp; r += 32) cp_async8(&S.V[c * LD + r], A + r + (size_t)c * ld, true);
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
         __syncthreads();
     }
     // S.ipiv / S.info are panel-relative here (row_off = 0): j is added on the way out

@@ -819,3 +819,41 @@ def test_fused_tail_structured_and_vbatched(gpu_queue, level):
             assert np.array_equal(out[offs[b]:offs[b + 1]].reshape(1, nn, m), ref), (b, m, nn)
     finally:
         mb.set_fused_tail(0)
+
+
+@pytest.mark.parametrize("shift", [0, 1])
+@pytest.mark.parametrize("m,n,ld", [(101, 77, 101), (127, 127, 127), (128, 128, 129), (255, 255, 257), (300, 64, 301), (511, 200, 511),
+                                    (96, 96, 97), (200, 333, 201), (65, 65, 65), (128, 128, 128), (256, 256, 256)])
+def test_any_alignment_tma_staging(gpu_queue, shift, m, n, ld):
+    """Odd m / ldda and matrices that start 8 bytes off a 16-byte boundary: the left-looking driver stages them by TMA through
+    parity-shifted shared-memory columns (left_update_kernel<NW, true>). Bit-exact, padding and the bytes around each matrix
+    untouched."""
+    import torch
+    batch = 5
+    A0, _ = oracle.random_batch(batch, m, n)
+    per = n * ld + 3  # an odd gap between matrices: their bases alternate between 0 and 8 mod 16
+    buf = torch.full((batch * per + 2,), -1.5, dtype=torch.float64, device="cuda")
+    host = np.full(batch * per + 2, -1.5)
+    for b in range(batch):
+        o = shift + b * per
+        blk = np.full((n, ld), 9.75)
+        blk[:, :m] = A0[b]
+        host[o:o + n * ld] = blk.reshape(-1)
+    buf.copy_(torch.from_numpy(host))
+    ptrs = torch.tensor([buf.data_ptr() + (shift + b * per) * 8 for b in range(batch)], dtype=torch.int64, device="cuda")
+    k = min(m, n)
+    ip = torch.zeros((batch, k), dtype=torch.int32, device="cuda")
+    ipp = torch.tensor([ip.data_ptr() + b * k * 4 for b in range(batch)], dtype=torch.int64, device="cuda")
+    info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    assert mb.magma_dgetrf_batched(m, n, ptrs, ld, ipp, info, batch, gpu_queue) == 0
+    gpu_queue.sync()
+    out = buf.cpu().numpy()
+    ref = A0.copy()
+    ipr, infr = oracle.getrf_batched(ref, m)
+    assert np.array_equal(ip.cpu().numpy(), ipr) and np.array_equal(info.cpu().numpy(), infr)
+    want = host.copy()
+    for b in range(batch):
+        o = shift + b * per
+        blk = want[o:o + n * ld].reshape(n, ld)
+        blk[:, :m] = ref[b]
+    assert np.array_equal(out, want)

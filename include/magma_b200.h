@@ -445,6 +445,9 @@ void magma_b200_set_chain_panel(int level);
  * kernel that updated them (no panel launch, no slab round trip), 2 = the last <= 32-row panel too, 0 = off (default:
  * four chains per SM in the slab kernel lose to the 8..12 of the panel kernels, n = 128: 8.99 -> 9.69 ms). */
 void magma_b200_set_fused_tail(int level);
+/* 1 (default): panels of 129..512 rows in the left-looking driver are factored in two 16-column halves per thread
+ * (twice the pivot chains per SM); 0: the 32-column register panel kernel (A/B runs). */
+void magma_b200_set_tall_panel(int on);
 /* 1 (default): magma_dgetri_outofplace_batched runs its single-launch kernel for n <= 64; 0: identity + getrs for every n. */
 void magma_b200_set_getri_fused(int on);
 /* Largest max(m,n) routed to the single-launch shared-memory tier (lu_fused.cu), 0..128; 0 disables it (A/B runs). */

@@ -205,6 +205,173 @@ panel_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__
 }
 
 // -------------------------------------------------------------------------------------------
+// Tall panels of the left-looking driver (129..512 rows) in two 16-column halves.
+// panel_kernel keeps a row's 32 columns in registers: 80 registers x 512 threads leave ONE pivot chain per SM at 512 rows
+// (two at 384, three at 256), and a tall panel's column costs ~1400 cycles (two CTA barriers) whatever else the SM could do:
+// 21% of the n = 512 call and of vbatched config 4. Here a thread holds 16 columns at a time:
+//   A  columns 0..15 factored as panel_kernel does (lazy positions, row published through shared memory), the results PARKED
+//      in shared memory (16 doubles per row: 64 KB at 512 rows; final places are not known before B);
+//   U  the 16 pivot rows publish their multipliers (L11) and their raw second halves; eight warps solve U12 = L11^-1 A12
+//      (two columns per warp, lane = row of the block, one shuffle per step); every other row applies the rank-16 update
+//      with its parked multipliers and U12 broadcast from shared memory -- k increasing per element, zero-pivot steps
+//      skipped: the canonical order;
+//   B  columns 16..31 factored the same way; both halves are then stored at the final places.
+// Half the registers per thread: two chains per SM at 512 rows, three at 384, four at 256. Outputs as panel_kernel's in the
+// left-looking driver (factors in final row order, pivots, step permutation record, info).
+// -------------------------------------------------------------------------------------------
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+panel2_kernel(Dims d, double **__restrict__ dA, int **__restrict__ dipiv, int *__restrict__ dinfo, int j, long batch,
+              const int *__restrict__ index_list, unsigned short *__restrict__ sinv, int sinv_rows, int sinv_blocks)
+{
+    constexpr int H = 16;
+    __shared__ unsigned long long cbits[2][32];
+    __shared__ int cpos[2][32];
+    __shared__ __align__(16) double prow[2][H + 2];  // [H] = 1/pivot
+    __shared__ int sipiv[2 * H];
+    __shared__ __align__(16) double U12[H][H];  // second halves of the 16 pivot rows, raw, then solved in place
+    __shared__ double L11[H][H + 1];             // L11[k][p], p < k: multipliers of the row that became pivot row k
+    __shared__ unsigned zmask_s;                 // bit i: step i met an exactly zero pivot (no scaling, no update)
+    extern __shared__ __align__(16) unsigned char p2_raw[];
+    double *park = reinterpret_cast<double *>(p2_raw);  // park[c * T + row]: the first half's results, rows in ORIGINAL order
+
+    const long slot = blockIdx.x;
+    const long b = index_list ? index_list[slot] : slot;
+    if (b < 0) return;
+    int m, n, ld;
+    dims_of(d, b, m, n, ld);
+    const int mn = m < n ? m : n;
+    if (j >= mn) return;
+    const int jb = (mn - j) < 32 ? (mn - j) : 32;
+    const int jb1 = jb < H ? jb : H, jb2 = jb - jb1;
+    const int T = (int)blockDim.x;
+    const int mp = m - j;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, wid = tid >> 5, nw = (int)blockDim.x >> 5;
+    double *__restrict__ A = dA[b] + (size_t)j + (size_t)j * ld;  // panel origin
+    const bool mine = tid < mp;
+    int pos = mine ? tid : NOPOS;  // current position of this thread's row (lazy interchanges)
+    double a[H];
+#pragma unroll
+    for (int c = 0; c < H; ++c) a[c] = (mine && c < jb1) ? A[tid + (size_t)c * ld] : 1.0;
+    if (tid == 0) zmask_s = 0;
+    int info = 0;
+
+    // cnt column steps on a[0..cnt): step i = ibase + ii works on a[ii]
+    auto chain = [&](const int ibase, const int cnt) {
+#pragma unroll
+        for (int ii = 0; ii < H; ++ii) {
+            if (ii < cnt) {
+                const int i = ibase + ii;
+                const bool act = (pos >= i) && (pos != NOPOS);
+                const unsigned long long lb = act ? ((unsigned long long)__double_as_longlong(a[ii]) & 0x7fffffffffffffffull) : 0ull;
+                const int lp = act ? pos : NOPOS;
+                const double rinv = rcp_fast_f64(a[ii]);  // every thread inverts its own candidate while the search runs
+                const int wl = warp_argmax_lane(lb, lp);
+                if (lane == wl) {
+                    cbits[i & 1][wid] = lb;
+                    cpos[i & 1][wid] = lp;
+                }
+                __syncthreads();
+                const unsigned long long eb = (lane < nw) ? cbits[i & 1][lane] : 0ull;
+                const int ep = (lane < nw) ? cpos[i & 1][lane] : NOPOS;
+                const int ppos = __shfl_sync(0xffffffffu, ep, warp_argmax_lane(eb, ep));  // position of the pivot row (>= i)
+                if (tid == 0) sipiv[i] = ppos;
+                if (lp == ppos) {
+#pragma unroll
+                    for (int c = 0; c < H; ++c)
+                        if (c >= ii) prow[i & 1][c] = a[c];
+                    // the inline reciprocal equals IEEE 1/x for |x| in [2^-999, 2^993); outside (one thread, rare) divide
+                    prow[i & 1][H] = rcp_fast_ok((unsigned)(lb >> 32)) ? rinv : 1.0 / a[ii];
+                }
+                if (pos == ppos) pos = i;
+                else if (pos == i) pos = ppos;
+                __syncthreads();
+                const double piv = prow[i & 1][ii];
+                if (piv == 0.0) {
+                    if (info == 0) info = i + 1;
+                    if (tid == 0) zmask_s |= 1u << i;
+                } else if (pos > i && pos != NOPOS) {
+                    const double l = a[ii] * prow[i & 1][H];
+                    a[ii] = l;
+#pragma unroll
+                    for (int c = 0; c < H; ++c)
+                        if (c > ii) a[c] = fma(-l, prow[i & 1][c], a[c]);
+                }
+            }
+        }
+    };
+
+    chain(0, jb1);
+    if (jb2 == 0) {
+        if (mine) {
+#pragma unroll
+            for (int c = 0; c < H; ++c)
+                if (c < jb1) A[pos + (size_t)c * ld] = a[c];
+        }
+    } else {
+        // jb1 == 16 here. Park the first half; the pivot rows publish their multipliers.
+        if (mine) {
+#pragma unroll
+            for (int c = 0; c < H; ++c) park[c * T + tid] = a[c];
+            if (pos < H) {
+#pragma unroll
+                for (int p = 0; p < H; ++p)
+                    if (p < pos) L11[pos][p] = a[p];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < H; ++c) a[c] = (mine && c < jb2) ? A[tid + (size_t)(H + c) * ld] : 1.0;
+        if (mine && pos < H) {
+#pragma unroll
+            for (int c = 0; c < H; ++c) U12[pos][c] = a[c];
+        }
+        __syncthreads();
+        const unsigned zm = zmask_s;
+        for (int cp = wid; cp < 8; cp += nw) {  // U12 = L11^-1 A12 in place: a warp takes columns 2 cp, 2 cp + 1; lane = (column, row k)
+            const int k = lane & 15, c = 2 * cp + (lane >> 4);
+            double x = U12[k][c];
+#pragma unroll
+            for (int p = 0; p < H - 1; ++p) {
+                const double xp = __shfl_sync(0xffffffffu, x, (lane & 16) | p);  // x(p) is final: every step q < p has been applied
+                if (k > p && !((zm >> p) & 1u)) x = fma(-L11[k][p], xp, x);
+            }
+            U12[k][c] = x;
+        }
+        __syncthreads();
+        if (mine) {
+            if (pos < H) {
+#pragma unroll
+                for (int c = 0; c < H; ++c) a[c] = U12[pos][c];
+            } else {
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    if (!((zm >> k) & 1u)) {
+                        const double l = park[k * T + tid];  // this row's parked multiplier of step k
+#pragma unroll
+                        for (int c = 0; c < H; ++c) a[c] = fma(-l, U12[k][c], a[c]);
+                    }
+                }
+            }
+        }
+        chain(H, jb2);
+        if (mine) {
+#pragma unroll
+            for (int c = 0; c < H; ++c)
+                if (c < jb2) A[pos + (size_t)(H + c) * ld] = a[c];
+#pragma unroll
+            for (int c = 0; c < H; ++c) A[pos + (size_t)c * ld] = park[c * T + tid];
+        }
+    }
+    if (mine) sinv[((size_t)slot * sinv_blocks + (j >> 5)) * sinv_rows + j + pos] = (unsigned short)(j + tid);
+    if (tid < jb) dipiv[b][j + tid] = j + sipiv[tid] + 1;
+    if (tid == 0) {
+        if (j == 0) dinfo[b] = info;
+        else if (info && dinfo[b] == 0) dinfo[b] = j + info;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
 // Panel factorisation straight on global memory: correctness fallback for panels taller than
 // the register kernel covers (m - j > 8192). One CTA per matrix, W columns. Interchanges are
 // physical here, so the record lists are rebuilt from the pivots by thread 0.
@@ -1791,6 +1958,28 @@ inline void launch_panel32(const Dims &d, double **dA, int **dipiv, int *dinfo, 
     count_launch();
 }
 
+// Tall panels (129..512 rows) of the left-looking driver: two 16-column halves per thread (panel2_kernel)
+inline void launch_panel2(const Dims &d, double **dA, int **dipiv, int *dinfo, int j, int T, long batch, const int *il,
+                          cudaStream_t s, unsigned short *sinv, int sinv_rows, int sinv_blocks)
+{
+    const size_t smem = (size_t)T * 16 * sizeof(double);  // the parked half
+    static DevOnce o192, o256, o384, o512;
+    if (T <= 192) {
+        smem_optin(o192, panel2_kernel<192, 6>, 192 * 16 * sizeof(double));
+        panel2_kernel<192, 6><<<(unsigned)batch, T, smem, s>>>(d, dA, dipiv, dinfo, j, batch, il, sinv, sinv_rows, sinv_blocks);
+    } else if (T <= 256) {
+        smem_optin(o256, panel2_kernel<256, 4>, 256 * 16 * sizeof(double));
+        panel2_kernel<256, 4><<<(unsigned)batch, T, smem, s>>>(d, dA, dipiv, dinfo, j, batch, il, sinv, sinv_rows, sinv_blocks);
+    } else if (T <= 384) {
+        smem_optin(o384, panel2_kernel<384, 3>, 384 * 16 * sizeof(double));
+        panel2_kernel<384, 3><<<(unsigned)batch, T, smem, s>>>(d, dA, dipiv, dinfo, j, batch, il, sinv, sinv_rows, sinv_blocks);
+    } else {
+        smem_optin(o512, panel2_kernel<512, 2>, 512 * 16 * sizeof(double));
+        panel2_kernel<512, 2><<<(unsigned)batch, T, smem, s>>>(d, dA, dipiv, dinfo, j, batch, il, sinv, sinv_rows, sinv_blocks);
+    }
+    count_launch();
+}
+
 // Two 32-column panels as one 64-wide step (panels <= 512 rows, both in the tiled regime). The trailing
 // matrix is read and written ONCE per 64 columns instead of once per 32 (the k = 32 update was HBM bound:
 // 87 GB per n = 512 call):
@@ -1954,6 +2143,9 @@ magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, i
                 // factored inside left_update_kernel
             } else if (!nopiv && T <= 128 && g_chain_panel > 0 && T > 128 - 32 * g_chain_panel) {
                 if ((rc = panel_chain_launch(d, dA, dipiv, dinfo, j, T, batch, il, s, sinv, sinv_rows, sinv_blocks)) != 0) return rc;
+            } else if (!nopiv && T > 128 && g_tall_panel2 && sinv) {
+                launch_panel2(d, dA, dipiv, dinfo, j, T, batch, il, s, sinv, sinv_rows, sinv_blocks);
+                MB200_CHECK_LAUNCH("panel2_kernel");
             } else {
                 launch_panel32(d, dA, dipiv, dinfo, recs, j, T, batch, il, s, sinv, sinv_rows, sinv_blocks, nopiv);
                 MB200_CHECK_LAUNCH("panel_kernel");

@@ -857,3 +857,29 @@ def test_any_alignment_tma_staging(gpu_queue, shift, m, n, ld):
         blk = want[o:o + n * ld].reshape(n, ld)
         blk[:, :m] = ref[b]
     assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("on", [0, 1])
+@pytest.mark.parametrize("m,n,batch", [(512, 512, 2), (384, 384, 2), (256, 256, 3), (200, 130, 3), (130, 200, 3), (129, 129, 4), (300, 40, 3),
+                                       (511, 77, 2), (160, 160, 3), (450, 300, 2), (257, 17, 3), (333, 333, 2)])
+def test_tall_panel_switch(gpu_queue, on, m, n, batch):
+    """Panels of 129..512 rows in the left-looking driver: two 16-column halves per thread (default) and the 32-column register
+    panel give the oracle's bits (square, tall, wide, odd, a narrow last panel of fewer than 16 columns)."""
+    mb.set_tall_panel(on)
+    try:
+        A0, _ = oracle.random_batch(batch, m, n)
+        check_against_oracle(gpu_queue, A0, m)
+    finally:
+        mb.set_tall_panel(1)
+
+
+def test_tall_panel_structured(gpu_queue):
+    """Singular columns in both halves of a tall panel, ties, identity / permutation inputs (zero-pivot steps are skipped by
+    the solve and by the rank-16 update exactly as the oracle skips them)."""
+    rng = np.random.default_rng(23)
+    n = 256
+    mats = [np.zeros((n, n)), np.ones((n, n)), np.eye(n), np.fliplr(np.eye(n)), rng.integers(-3, 4, size=(n, n)).astype(float)]
+    Z = rng.random((n, n)); Z[:, 5] = 0.0; Z[:, 20] = 0.0; Z[:, 100] = 0.0; Z[:, 117] = 0.0; mats.append(Z)
+    Z2 = rng.random((n, n)); Z2[n // 2:, :] = Z2[:n - n // 2, :]; mats.append(Z2)
+    Z3 = rng.random((n, n)); Z3[:, :3] = 0.0; mats.append(Z3)
+    check_against_oracle(gpu_queue, np.stack(mats), n)

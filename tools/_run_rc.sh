@@ -1,4 +1,4 @@
-timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "test_left_looking_4_warps and 128-128 or test_getrf_blocked_square and 256 or test_left_looking_16_warps and 400 or test_chain_panel_switch and 3-128-128 or test_fused_tail_switch and 2-128-128 or test_fused_tier_full_size_sample or test_getri_fused and 64-64-64 or test_getri_fused and 31-31 or test_getrf_batched_prec and 100-100 and z or test_getrf_batched_prec and 32-32-32 and c or test_getrs_batched_prec and 50-4-111-s" > gpurun_out/racecheck.log 2>&1; echo "racecheck rc $?" >> gpurun_out/racecheck.log
-tail -5 gpurun_out/racecheck.log
-for rep in 1 2; do python tools/fused_time.py 128 50000 3 | sort -t' ' -k3 -n | head -1; MB200_LIB=$PWD/magma_b200/lib/libmagma_b200_prev.so python tools/fused_time.py 128 50000 3 | sort -t' ' -k3 -n | head -1; done
-python tools/vbatched_time.py 3; EVEN=1 python tools/vbatched_time.py 3
+timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "test_tall_panel_switch and 1-512-512 or test_tall_panel_switch and 1-200-130 or test_tall_panel_structured or test_any_alignment_tma_staging and 255-255-257 or test_any_alignment_tma_staging and 101-77-101" > gpurun_out/racecheck2.log 2>&1; echo "racecheck rc $?" >> gpurun_out/racecheck2.log
+tail -4 gpurun_out/racecheck2.log
+timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "tall_panel or any_alignment" > gpurun_out/memcheck2.log 2>&1; echo "memcheck rc $?" >> gpurun_out/memcheck2.log
+tail -4 gpurun_out/memcheck2.log

@@ -578,6 +578,41 @@ def run_sweep(mb, torch, np, q, local, rank, world, barrier, max_over_ranks, sum
 
     nopiv("F2 dgetrf_nopiv_batched n=128 batch=50000", 128, 50_000)
 
+    # G1-G3: the standalone batched BLAS-3 behind the reference names and the butterfly solver.
+    # flops: 2mnk (gemm), m^2 n (trsm, testing/flops.h FLOPS_DTRSM left); bytes: every operand once in, the result once out.
+    def blas3(reps=5):
+        dev = torch.device("cuda", local)
+        g = torch.Generator(device=dev)
+        g.manual_seed(61 + rank)
+        idx = lambda cnt: torch.arange(cnt, dtype=torch.int64, device=dev)  # noqa: E731
+        # G1: C <- C - A B (the LU update's alpha = -1, beta = 1), 128 x 128 x 128
+        n, batch = 128, 20_000
+        A, B, Cm = (torch.rand((batch, n, n), dtype=torch.float64, device=dev, generator=g) for _ in range(3))
+        pa, pb, pc = (idx(batch) * (n * n * 8) + t.data_ptr() for t in (A, B, Cm))
+        fn = lambda: (mb.magma_dgemm_batched_core(111, 111, n, n, n, -1.0, pa, 0, 0, n, pb, 0, 0, n, 1.0, pc, 0, 0, n, batch, q), 0)[1]  # noqa: E731
+        med, best = timed(fn, lambda: None, reps)
+        fl = 2.0 * n * n * n
+        roof = min(fl / (4 * 8.0 * n * n) * hbm_peak, fp64_peak)
+        out.append({"config": "G1 dgemm_batched NN n=128 batch=20000 (alpha=-1, beta=1)", "n": n, "batch_per_gpu": batch, "ms": med,
+                    "ms_best": best, "gflops": fl * batch * world / (med * 1e-3) / 1e9, "gflops_per_gpu": fl * batch / (med * 1e-3) / 1e9,
+                    "roofline_gflops": roof, "frac_of_roofline": fl * batch / (med * 1e-3) / 1e9 / roof})
+        # G2: B <- L^-1 B, unit lower, left, 128 x 128 triangle, 64 right-hand sides
+        m, nr = 128, 64
+        Bm = torch.rand((batch, nr, m), dtype=torch.float64, device=dev, generator=g)
+        B0 = Bm.clone()
+        pb2 = idx(batch) * (nr * m * 8) + Bm.data_ptr()
+        fn = lambda: (mb.magmablas_dtrsm_batched(141, 122, 111, 132, m, nr, 1.0, pa, n, pb2, m, batch, q), 0)[1]  # noqa: E731
+        med, best = timed(fn, lambda: Bm.copy_(B0), reps)
+        fl = float(m) * m * nr
+        roof = min(fl / (8.0 * (m * m / 2 + 2 * m * nr)) * hbm_peak, fp64_peak)
+        out.append({"config": "G2 dtrsm_batched L,Lower,NoTrans,Unit m=128 n=64 batch=20000", "n": m, "batch_per_gpu": batch, "ms": med,
+                    "ms_best": best, "gflops": fl * batch * world / (med * 1e-3) / 1e9, "gflops_per_gpu": fl * batch / (med * 1e-3) / 1e9,
+                    "roofline_gflops": roof, "frac_of_roofline": fl * batch / (med * 1e-3) / 1e9 / roof})
+        del A, B, Cm, Bm, B0
+        torch.cuda.empty_cache()
+
+    blas3()
+
     # P1-P3: the s / c / z entry points (csrc/lu_scz.cu: coverage kernels, not tuned to the roofline).
     # bytes: read + write the matrix in its own element size; flops: real = FLOPS_DGETRF, complex = 4x (testing/flops.h:24-27)
     def prec(name, p, n, batch, reps=5):

@@ -365,8 +365,11 @@ __device__ __forceinline__ void getrs_sweep(double (&acc)[RT][2][2], double *Xs,
 template <int RT>  // row tiles (8 rows) per warp: n <= 64 * RT
 __global__ void __launch_bounds__(SOLVE_THREADS, 2)
 getrs_dmma_kernel(int n, int nrhs, double **__restrict__ dA, int ldda, int **__restrict__ dipiv,
-                  double **__restrict__ dB, int lddb, int rhs_tiles)
+                  double **__restrict__ dB, int lddb, int rhs_tiles, int mode, double alpha)
 {
+    // mode 0: getrs (both sweeps); 1: forward sweep only = trsm Left / Lower / NoTrans / Unit; 2: backward sweep only = trsm
+    // Left / Upper / NoTrans / NonUnit (multiply by the inverted diagonal, as the reference's trsm). alpha scales B on the way
+    // in (BLAS dtrsm order); the getrs path passes exactly 1.0.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *Xs = reinterpret_cast<double *>(smem_raw);  // [32][XW]
     double *Ts = Xs + 32 * XW;                           // [2][32*32]
@@ -385,7 +388,9 @@ getrs_dmma_kernel(int n, int nrhs, double **__restrict__ dA, int ldda, int **__r
     const int ld = ldda;
     const int nblk = (n + 31) / 32;
 
-    stage_diag(Ts, A, ld, n, 0);
+    // the first diagonal block of the sequence, where the sweep that runs first expects it (getrs_sweep: Ts + (seq & 1) * 1024)
+    if (mode == 2) stage_diag(Ts + (nblk & 1) * 1024, A, ld, n, 32 * (nblk - 1));
+    else stage_diag(Ts, A, ld, n, 0);
     build_perm_par(n, dipiv ? dipiv[b] : nullptr, perm, sipiv);
 
     // right-hand sides -> accumulator fragments, interchanges applied on the way in
@@ -399,13 +404,14 @@ getrs_dmma_kernel(int n, int nrhs, double **__restrict__ dA, int ldda, int **__r
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int c = 8 * jt + 2 * q + e;
-                acc[i][jt][e] = (r < n && c < tr) ? B[pr + (size_t)c * lddb] : 0.0;
+                acc[i][jt][e] = (r < n && c < tr) ? alpha * B[pr + (size_t)c * lddb] : 0.0;
             }
     }
 
     // L y = P b (unit lower, blocks ascending), then U x = y (blocks descending)
-    getrs_sweep<true, RT>(acc, Xs, Ts, A, ld, n, nblk, w, lane, g, q);
-    getrs_sweep<false, RT>(acc, Xs, Ts, A, ld, n, nblk, w, lane, g, q);
+    if (mode != 2) getrs_sweep<true, RT>(acc, Xs, Ts, A, ld, n, nblk, w, lane, g, q);
+    if (mode != 1) getrs_sweep<false, RT>(acc, Xs, Ts, A, ld, n, nblk, w, lane, g, q);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");  // mode 1 leaves the turn block's prefetch in flight
 
 #pragma unroll
     for (int i = 0; i < RT; ++i) {
@@ -543,9 +549,9 @@ magma_int_t getrs_launch(int trans, int n, int nrhs, double **dA, int ldda, int 
         if (grid > 0x7fffffffL) return MAGMA_ERR_NOT_SUPPORTED;
         const size_t smem = sizeof(double) * (32 * XW + 2 * 1024) + sizeof(int) * 2 * (size_t)n;
         if (n <= 256)
-            getrs_dmma_kernel<4><<<(unsigned)grid, SOLVE_THREADS, smem, s>>>(n, nrhs, dA, ldda, dipiv, dB, lddb, rhs_tiles);
+            getrs_dmma_kernel<4><<<(unsigned)grid, SOLVE_THREADS, smem, s>>>(n, nrhs, dA, ldda, dipiv, dB, lddb, rhs_tiles, 0, 1.0);
         else
-            getrs_dmma_kernel<8><<<(unsigned)grid, SOLVE_THREADS, smem, s>>>(n, nrhs, dA, ldda, dipiv, dB, lddb, rhs_tiles);
+            getrs_dmma_kernel<8><<<(unsigned)grid, SOLVE_THREADS, smem, s>>>(n, nrhs, dA, ldda, dipiv, dB, lddb, rhs_tiles, 0, 1.0);
         count_launch();
         MB200_CHECK_LAUNCH("getrs_dmma_kernel");
         return 0;
@@ -582,6 +588,28 @@ void trsm_left_launch(int uplo, int trans, int diag, int m, int n, double alpha,
                       double **dB, int lddb, long batch, cudaStream_t s)
 {
     if (m <= 0 || n <= 0 || batch <= 0) return;
+    // the two solves of an LU -- unit lower forward, non-unit upper backward -- run on the getrs kernel's tensor-pipe sweeps
+    // (one sweep each): same canonical order, bit-identical to the shared-memory solver below
+    // (m = 128, n = 64, 20000 matrices: 12.7 ms there)
+    const bool fwd_unit = uplo == MagmaLower && trans == MagmaNoTrans && diag == MagmaUnit;
+    const bool bwd_nonunit = uplo == MagmaUpper && trans == MagmaNoTrans && diag == MagmaNonUnit;
+    if ((fwd_unit || bwd_nonunit) && m > 32 && m <= 512 && g_tier != 4) {
+        const int rhs_tiles = (n + 15) / 16;
+        const size_t smem_d = sizeof(double) * (32 * XW + 2 * 1024) + sizeof(int) * 2 * (size_t)m;
+        const long per = 0x7fffffffL / rhs_tiles;
+        for (long off = 0; off < batch; off += per) {
+            const long cnt = batch - off < per ? batch - off : per;
+            if (m <= 256)
+                getrs_dmma_kernel<4><<<(unsigned)(cnt * rhs_tiles), SOLVE_THREADS, smem_d, s>>>(m, n, dA + off, ldda, nullptr, dB + off, lddb,
+                                                                                             rhs_tiles, fwd_unit ? 1 : 2, alpha);
+            else
+                getrs_dmma_kernel<8><<<(unsigned)(cnt * rhs_tiles), SOLVE_THREADS, smem_d, s>>>(m, n, dA + off, ldda, nullptr, dB + off, lddb,
+                                                                                             rhs_tiles, fwd_unit ? 1 : 2, alpha);
+            count_launch();
+            MB200_CHECK_LAUNCH_VOID("getrs_dmma_kernel (trsm)");
+        }
+        return;
+    }
     size_t smem;
     const int tr = pick_tr(m, n, smem);
     if (tr == 0) {

@@ -883,3 +883,38 @@ def test_tall_panel_structured(gpu_queue):
     Z2 = rng.random((n, n)); Z2[n // 2:, :] = Z2[:n - n // 2, :]; mats.append(Z2)
     Z3 = rng.random((n, n)); Z3[:, :3] = 0.0; mats.append(Z3)
     check_against_oracle(gpu_queue, np.stack(mats), n)
+
+
+@pytest.mark.parametrize("m,n", [(33, 5), (64, 16), (128, 64), (200, 17), (257, 40), (512, 16)])
+@pytest.mark.parametrize("which", ["lower_unit", "upper_nonunit"])
+def test_dtrsm_left_on_the_tensor_pipe(gpu_queue, which, m, n):
+    """The two solves of an LU through magmablas_dtrsm_batched (side = Left): one sweep of the getrs DMMA kernel, bit-identical
+    to the shared-memory DFMA solver (tier 4 forces it) and close to numpy; alpha applied on the way in."""
+    import torch
+    rng = np.random.default_rng(m + n)
+    batch = 3
+    T = rng.random((batch, m, m)) + 4 * np.eye(m)   # stored column-major: T[b].T is the matrix
+    B = rng.random((batch, n, m + 2))               # lddb = m + 2
+    uplo, diag = (mb.MagmaLower, mb.MagmaUnit) if which == "lower_unit" else (mb.MagmaUpper, mb.MagmaNonUnit)
+    dT = torch.from_numpy(T).cuda()
+    pT = torch.tensor([dT.data_ptr() + 8 * m * m * b for b in range(batch)], dtype=torch.int64, device="cuda")
+    out = {}
+    for alpha in (1.0, -0.5):
+        for tier in (0, 4):
+            mb.set_tier(tier)
+            try:
+                dB = torch.from_numpy(B).cuda()
+                pB = torch.tensor([dB.data_ptr() + 8 * (m + 2) * n * b for b in range(batch)], dtype=torch.int64, device="cuda")
+                mb.magmablas_dtrsm_batched(mb.MagmaLeft, uplo, mb.MagmaNoTrans, diag, m, n, alpha, pT, m, pB, m + 2, batch, gpu_queue)
+                gpu_queue.sync()
+                out[(alpha, tier)] = dB.cpu().numpy()
+            finally:
+                mb.set_tier(0)
+        X = out[(alpha, 0)]
+        assert np.array_equal(X, out[(alpha, 4)])
+        assert np.array_equal(X[:, :, m:], B[:, :, m:])  # padding rows untouched
+        for b in range(batch):
+            Tm = T[b].T
+            Tm = (np.tril(Tm, -1) + np.eye(m)) if which == "lower_unit" else np.triu(Tm)
+            ref = np.linalg.solve(Tm, alpha * B[b, :, :m].T)
+            assert np.allclose(X[b, :, :m].T, ref, rtol=1e-9, atol=1e-11)

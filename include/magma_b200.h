@@ -448,6 +448,10 @@ void magma_b200_set_fused_tail(int level);
 /* 1 (default): panels of 129..512 rows in the left-looking driver are factored in two 16-column halves per thread
  * (twice the pivot chains per SM); 0: the 32-column register panel kernel (A/B runs). */
 void magma_b200_set_tall_panel(int on);
+/* Left-looking driver: the batch is cut into `parts` slices (1..4) that run their kernel chains on separate streams, forked
+ * from and joined to the queue's stream, so that the tail of every kernel is filled by another slice's work. 0 (default):
+ * two slices for matrices of more than 256 rows (n = 512: 25.45 -> 24.76 ms), one below (where it costs 1-2%); 1 = off. */
+void magma_b200_set_split(int parts);
 /* 1 (default): magma_dgetri_outofplace_batched runs its single-launch kernel for n <= 64; 0: identity + getrs for every n. */
 void magma_b200_set_getri_fused(int on);
 /* Largest max(m,n) routed to the single-launch shared-memory tier (lu_fused.cu), 0..128; 0 disables it (A/B runs). */

@@ -97,6 +97,7 @@ SIGNATURES = {
     "magma_b200_set_chain_panel": (None, [i32]),
     "magma_b200_set_fused_tail": (None, [i32]),
     "magma_b200_set_tall_panel": (None, [i32]),
+    "magma_b200_set_split": (None, [i32]),
     "magma_b200_set_getri_fused": (None, [i32]),
     "magma_sgetrf_batched": (i32, [i32, i32, vp, i32, vp, vp, i32, vp]),
     "magma_sgetrs_batched": (i32, [i32, i32, i32, vp, i32, vp, vp, i32, i32, vp]),

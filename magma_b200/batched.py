@@ -225,6 +225,10 @@ def set_chain_panel(on: int):
     _lib.load().magma_b200_set_chain_panel(on)
 
 
+def set_split(parts: int):
+    _lib.load().magma_b200_set_split(parts)
+
+
 def set_tall_panel(on: int):
     _lib.load().magma_b200_set_tall_panel(on)
 

@@ -162,6 +162,7 @@ long rcp_selftest_run(long n, cudaStream_t s);
 magma_int_t panel_chain_launch(const Dims &d, double **dA, int **dipiv, int *dinfo, int j, int T, long batch, const int *il,
                                cudaStream_t s, unsigned short *sinv, int sinv_rows, int sinv_blocks);
 extern std::atomic<int> g_fused_tail;   // left-looking driver, at most 128 rows: panels factored in the slab kernel's tail (0 off = default: measured slower; 1: 33..96 rows, 2: <= 96 rows)
+extern std::atomic<int> g_split;        // left-looking driver: the batch runs as this many independent parts on their own streams (0 = auto: 2 above 256 rows; 1 = off)
 extern std::atomic<int> g_tall_panel2;  // left-looking driver: panels of 129..512 rows in two 16-column halves (panel2_kernel); 0: panel_kernel
 extern std::atomic<int> g_chain_panel;  // level L > 0: panels of (128 - 32 L, 128] rows go to panel_chain_launch (default 3); 0: panel_kernel
 

@@ -31,6 +31,9 @@
 //                   interchanges replayed from ipiv.
 // All arithmetic is in the canonical order of oracle/lu_oracle.c: bit-identical factors.
 #include "lu_chain.cuh"
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace mb200 {
 
@@ -2114,8 +2117,8 @@ namespace {
 
 // Left-looking driver (max_m <= 512): per 32-column slab one update kernel (everything to its left, once)
 // and one panel kernel; the interchanges of the L columns in one pass at the end.
-magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo, PivRec *recs,
-                             unsigned short *sinv, long batch, const int *il, cudaStream_t s, int nopiv)
+magma_int_t run_left_looking_one(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo, PivRec *recs,
+                                 unsigned short *sinv, long batch, const int *il, cudaStream_t s, int nopiv)
 {
     const int max_mn = max_m < max_n ? max_m : max_n;
     const int sinv_rows = ((max_m + 31) / 32) * 32, sinv_blocks = (max_mn + 31) / 32;
@@ -2167,6 +2170,68 @@ magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, i
         MB200_CHECK_LAUNCH("laswp_left_sinv_kernel");
     }
     return 0;
+}
+
+// Helper streams of the batch split below, one set per (device, caller stream); created on first use, kept for the process.
+struct SplitCtx {
+    cudaStream_t st[3];
+    cudaEvent_t fork, join[3];
+};
+SplitCtx &split_ctx(cudaStream_t s)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, SplitCtx> ctxs;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = ctxs.find({dev, s});
+    if (it == ctxs.end()) {
+        SplitCtx c;
+        for (int i = 0; i < 3; ++i) {
+            cudaStreamCreateWithFlags(&c.st[i], cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&c.join[i], cudaEventDisableTiming);
+        }
+        cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming);
+        it = ctxs.emplace(std::make_pair(dev, s), c).first;
+    }
+    return it->second;
+}
+
+// The left-looking flow is a strict chain of kernels per matrix -- panel, slab update, panel, ... -- that alternate between
+// two kinds of work: pivot chains (latency-bound, a third of the issue slots used) and DMMA slab updates. Matrices are
+// independent, so the batch is cut into g_split parts that run the same chain on their own streams: while one part is in a
+// panel kernel another is in a slab update, the SMs hold CTAs of both kinds, and every kernel's tail is filled by the other
+// parts' work. Scratch records are addressed by position in the batch, so each part simply takes its slice.
+magma_int_t run_left_looking(const Dims &d, int max_m, int max_n, double **dA, int **dipiv, int *dinfo, PivRec *recs,
+                             unsigned short *sinv, long batch, const int *il, cudaStream_t s, int nopiv)
+{
+    // Measured (same box): a kernel whose grid exceeds the SMs' CTA slots keeps the block scheduler to itself until its
+    // tail, so the overlap is the tails only. Two parts pay where a CTA fills an SM (more than 256 rows: n = 512 25.45 ->
+    // 24.76 ms, 27 waves of 148 CTAs per kernel) and cost 1-2% below that (n = 128 8.99 -> 9.14, n = 256 16.12 -> 16.37):
+    // g_split = 0 (default) splits in two above 256 rows only; 1..4 force a part count.
+    int parts = g_split;
+    if (parts <= 0) parts = max_m > 256 ? 2 : 1;
+    if (parts > 4) parts = 4;
+    while (parts > 1 && batch < (long)parts * 1184) --parts;  // at least eight CTAs per SM and part
+    if (parts <= 1) return run_left_looking_one(d, max_m, max_n, dA, dipiv, dinfo, recs, sinv, batch, il, s, nopiv);
+    const int max_mn = max_m < max_n ? max_m : max_n;
+    const size_t sinv_per = (size_t)(((max_m + 31) / 32) * 32) * (size_t)((max_mn + 31) / 32);
+    SplitCtx &c = split_ctx(s);
+    cudaEventRecord(c.fork, s);
+    magma_int_t rc = 0;
+    for (int p = 0; p < parts && rc == 0; ++p) {
+        const long lo = batch * p / parts, hi = batch * (p + 1) / parts;
+        cudaStream_t sp = p == 0 ? s : c.st[p - 1];
+        if (p > 0) cudaStreamWaitEvent(sp, c.fork, 0);
+        rc = run_left_looking_one(d, max_m, max_n, il ? dA : dA + lo, il ? dipiv : (dipiv ? dipiv + lo : nullptr), il ? dinfo : dinfo + lo,
+                                  recs ? recs + lo : nullptr, sinv ? sinv + (size_t)lo * sinv_per : nullptr, hi - lo,
+                                  il ? il + lo : nullptr, sp, nopiv);
+        if (p > 0) {
+            cudaEventRecord(c.join[p - 1], sp);
+            cudaStreamWaitEvent(s, c.join[p - 1], 0);
+        }
+    }
+    return rc;
 }
 
 }  // namespace

@@ -13,6 +13,7 @@ std::atomic<int> g_tier{0};
 std::atomic<int> g_chain_panel{3};
 std::atomic<int> g_fused_tail{0};
 std::atomic<int> g_tall_panel2{1};
+std::atomic<int> g_split{0};
 static std::atomic<int> g_init_count{0};
 
 #ifdef MB200_INTERPOSE
@@ -464,4 +465,5 @@ void magma_b200_set_small_rows(int rows) { g_small_rows = rows; }
 void magma_b200_set_chain_panel(int on) { g_chain_panel = on; }
 void magma_b200_set_fused_tail(int level) { g_fused_tail = level; }
 void magma_b200_set_tall_panel(int on) { g_tall_panel2 = on; }
+void magma_b200_set_split(int parts) { g_split = parts; }
 }  // extern "C"

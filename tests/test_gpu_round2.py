@@ -918,3 +918,26 @@ def test_dtrsm_left_on_the_tensor_pipe(gpu_queue, which, m, n):
             Tm = (np.tril(Tm, -1) + np.eye(m)) if which == "lower_unit" else np.triu(Tm)
             ref = np.linalg.solve(Tm, alpha * B[b, :, :m].T)
             assert np.allclose(X[b, :, :m].T, ref, rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("parts", [1, 2, 3, 4])
+@pytest.mark.parametrize("m,n,batch", [(128, 128, 9000), (300, 300, 2600), (64, 64, 5000)])
+def test_batch_split_streams(gpu_queue, parts, m, n, batch):
+    """The left-looking chain run as 1..4 slices of the batch on separate streams (forked from / joined to the queue's stream):
+    identical bits on a bit-exact sample of every slice, residual on all."""
+    mb.set_split(parts)
+    try:
+        A0, _ = oracle.random_batch(batch, m, n)
+        db = mb.DeviceBatch(batch, m, n, queue=gpu_queue)
+        db.upload(A0)
+        assert db.getrf() == 0
+        LU, ipiv, info = db.download()
+        assert not info.any()
+        sel = np.unique(np.concatenate([np.arange(0, batch, max(1, batch // 40)), np.arange(batch - 8, batch),
+                                        np.arange(batch // 2 - 4, batch // 2 + 4), np.arange(batch // 3 - 2, batch // 3 + 2)]))
+        ref = np.ascontiguousarray(A0[sel])
+        ipr, _ = oracle.getrf_batched(ref, m)
+        assert np.array_equal(LU[sel], ref) and np.array_equal(ipiv[sel], ipr)
+        assert oracle.lu_backward_error(A0, LU, ipiv, m) < oracle.TOL
+    finally:
+        mb.set_split(0)

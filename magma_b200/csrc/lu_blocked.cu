@@ -1842,7 +1842,8 @@ magma_int_t launch_left_update(const Dims &d, double **dA, unsigned short *sinv,
     static int ahead = -1;
     if (ahead < 0) {
         const char *e = getenv("MB200_LL_AHEAD");  // tuning sweeps
-        ahead = e ? atoi(e) : 2;  // measured: 1, 2, 3 within 3% of each other (n = 512: 34.5 / 34.4 / 35.6 ms)
+        // measured with the TMA chunks (ahead = 1 / 2 / 3): n = 512 25.58 / 24.76 / 25.01 ms, n = 256 16.27 / 16.12 / 15.92
+        ahead = e ? atoi(e) : (NW == 8 ? 3 : 2);
         if (ahead < 1) ahead = 1;
         if (ahead > LeftSmem<NW>::RING - 1) ahead = LeftSmem<NW>::RING - 1;
     }
